@@ -1,0 +1,215 @@
+/*
+ * ubs_b200.h -- C ABI of libubs_b200.so, the B200 (sm_100a) rasteriser for Universal Beta Splatting.
+ *
+ * Boundary contract
+ *   - extern "C", plain pointers and sizes, no torch / ATen types.  Every pointer is a DEVICE pointer unless
+ *     its name starts with `h_`.  The caller owns all memory (PyTorch allocates, passes data_ptr()).
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and asynchronous.  No entry point
+ *     synchronises the host unless documented.
+ *   - Every function returns 0 on success or a negative UBS_E* code; ubs_last_error() returns a thread-local
+ *     message for the last failure.  No exceptions cross the ABI.
+ *   - FP32 arithmetic throughout; radii/tile counts/offsets/ids are int32, intersection keys int64, matching
+ *     the reference dtypes (reference: submodules/gsplat/cuda/csrc/bindings.h:34-273).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to
+ * /root/reference/submodules/gsplat/cuda/csrc unless stated otherwise).
+ */
+#ifndef UBS_B200_H
+#define UBS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UBS_OK 0
+#define UBS_EINVAL (-1)   /* bad argument (null pointer, unsupported size)            */
+#define UBS_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed               */
+#define UBS_ENOSPC (-3)   /* caller-provided capacity / workspace too small            */
+#define UBS_EUNSUPPORTED (-4)
+
+#define UBS_MAX_CHANNELS 32 /* colour channels handled by one compositing launch      */
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+const char *ubs_last_error(void);
+int ubs_version(void);           /* ABI version, bumped on any signature change                          */
+int ubs_device_sm_count(void);   /* multiProcessorCount of the current device (grid sizing), <0 on error */
+
+/* ---- K1: skew parameters -> first-order rotation ------------------------------------------------------ */
+/* replaces l_triangle_to_rotmat_{fwd,bwd}_tensor (bindings.h:68-75; l_triagnle_to_rotmat_fwd.cu:8-36,
+ * l_triagnle_to_rotmat_bwd.cu:8-25).  l_triangle [N,3] -> rot [N,3,3] = I + skew(a01,a02,a12).            */
+int ubs_l_triangle_to_rotmat_fwd(int64_t N, const float *l_triangle, float *rot, void *stream);
+int ubs_l_triangle_to_rotmat_bwd(int64_t N, const float *v_rot, float *v_l_triangle, void *stream);
+
+/* ---- K2: (rot, scale, l_triangle) -> covariance ------------------------------------------------------- */
+/* replaces rot_scale_l_triangle_to_covar_{fwd,bwd}_tensor (bindings.h:49-66;
+ * rot_scale_l_triangle_to_covar_fwd.cu:8-188, ..._bwd.cu:8-235).  The strictly-lower entries of L follow
+ * torch.tril_indices(D, D, -1) order (the only layout the reference caller ever builds:
+ * scene/beta_model.py:69-73); D in [3, 8].  spatial_block != 0 -> only the 3x3 block is produced/consumed.  */
+int ubs_rot_scale_l_triangle_to_covar_fwd(int64_t N, int D, int spatial_block, const float *rot, /* [N,9] */
+                                          const float *scale,                                     /* [N,D] */
+                                          const float *l_triangle, /* [N, D(D-1)/2] */
+                                          float *covar,            /* [N,d,d], d = spatial ? 3 : D */
+                                          void *stream);
+int ubs_rot_scale_l_triangle_to_covar_bwd(int64_t N, int D, int spatial_block, const float *rot, const float *scale,
+                                          const float *l_triangle, const float *v_covar, /* [N,d,d] */
+                                          float *v_rot,                                   /* [N,9] */
+                                          float *v_scale,                                 /* [N,D] */
+                                          float *v_l_triangle,                            /* [N,D(D-1)/2] */
+                                          void *stream);
+
+/* ---- K3/K4: conditioning on the query (view direction [+ time]) --------------------------------------- */
+/* replaces cond_mean_convariance_opacity_{fwd,bwd}_tensor (bindings.h:34-47;
+ * cond_mean_convariance_opacity_fwd.cu:106-290, ..._bwd.cu:101-563).  D in [4, 8], Cd = D-3.
+ * No gradient is produced for `query` (reference: cuda/_wrapper.py:611).                                    */
+int ubs_cond_mean_covar_opacity_fwd(int64_t N, int D, const float *means, /* [N,D]   */
+                                    const float *covars,                  /* [N,D,D] */
+                                    const float *opacities,               /* [N]     */
+                                    const float *betas,                   /* [N,Cd]  */
+                                    const float *query,                   /* [N,Cd]  */
+                                    float *out_means,                     /* [N,3]   */
+                                    float *out_covars,                    /* [N,3,3] */
+                                    float *out_opacities,                 /* [N]     */
+                                    void *stream);
+int ubs_cond_mean_covar_opacity_bwd(int64_t N, int D, const float *means, const float *covars, const float *opacities,
+                                    const float *betas, const float *query, const float *v_out_means, /* [N,3]   */
+                                    const float *v_out_covars,                                        /* [N,3,3] */
+                                    const float *v_out_opacities,                                     /* [N]     */
+                                    float *v_means,                                                   /* [N,D]   */
+                                    float *v_covars,                                                  /* [N,D,D] */
+                                    float *v_opacities,                                               /* [N]     */
+                                    float *v_betas,                                                   /* [N,Cd]  */
+                                    void *stream);
+
+/* ---- K5/K6: world -> screen projection ---------------------------------------------------------------- */
+/* replaces fully_fused_projection_{fwd,bwd}_tensor, covars path, perspective camera (bindings.h:129-178;
+ * fully_fused_projection_fwd.cu:19-177, ..._bwd.cu:19-240).  Culled entries get radii = 0 and ZEROED outputs
+ * (the reference leaves them uninitialised).  compensations / v_compensations may be NULL.                   */
+int ubs_projection_fwd(int C, int64_t N, const float *means, /* [N,3] */
+                       const float *covars,                  /* [N,6] xx,xy,xz,yy,yz,zz */
+                       const float *viewmats,                /* [C,4,4] world->camera, row-major */
+                       const float *Ks,                      /* [C,3,3] */
+                       int width, int height, float eps2d, float near_plane, float far_plane, float radius_clip,
+                       int32_t *radii,       /* [C,N]   */
+                       float *means2d,       /* [C,N,2] */
+                       float *depths,        /* [C,N]   */
+                       float *conics,        /* [C,N,3] */
+                       float *compensations, /* [C,N] or NULL */
+                       void *stream);
+int ubs_projection_bwd(int C, int64_t N, const float *means, const float *covars, const float *viewmats,
+                       const float *Ks, int width, int height, float eps2d, const int32_t *radii,
+                       const float *conics, const float *compensations, /* NULL ok */
+                       const float *v_means2d, const float *v_depths, const float *v_conics,
+                       const float *v_compensations, /* NULL ok */
+                       float *v_means,               /* [N,3]  accumulated over cameras (zeroed by callee) */
+                       float *v_covars,              /* [N,6]  (xx, xy+yx, xz+zx, yy, yz+zy, zz)          */
+                       float *v_viewmats,            /* [C,4,4] or NULL                                   */
+                       void *stream);
+
+/* ---- K7-K9: tile intersection, onesweep radix sort, tile offsets --------------------------------------- */
+/* replaces isect_tiles_tensor + isect_offset_encode_tensor (bindings.h:180-199; isect_tiles.cu:16-333).
+ * Two-phase so that the caller can size the exact outputs (the reference syncs the host the same way,
+ * isect_tiles.cu:180-181), or skip the sync by passing a capacity bound.
+ *
+ *   ubs_isect_workspace_bytes(C*N, capacity)  -> bytes of scratch the next two calls need
+ *   ubs_isect_count(...)       tiles_per_gauss[C,N], *n_isects (device int64) ; no host sync
+ *   ubs_isect_emit_sort(...)   emits (key,val) pairs, stable LSD onesweep sort on bits
+ *                              [0, 32+tile_n_bits+cam_n_bits), writes offsets[C,th,tw].
+ *                              capacity = size of isect_ids / flatten_ids in elements; if *n_isects exceeds it
+ *                              nothing past capacity is written and *status (device int32) gets bit 0 set.
+ * key = cam << (32+tb) | tile << 32 | (int64)(int32)float_bits(depth) ; val = cam*N + prim.                  */
+size_t ubs_isect_workspace_bytes(int64_t CN, int64_t capacity);
+int ubs_isect_count(int C, int64_t N, const float *means2d, const int32_t *radii, int tile_size, int tile_width,
+                    int tile_height, int32_t *tiles_per_gauss, /* [C,N] */
+                    int64_t *n_isects,                         /* [1] device */
+                    void *workspace, size_t workspace_bytes, void *stream);
+int ubs_isect_emit_sort(int C, int64_t N, const float *means2d, const int32_t *radii, const float *depths,
+                        int tile_size, int tile_width, int tile_height, int do_sort,
+                        const int32_t *tiles_per_gauss, /* from ubs_isect_count */
+                        const int64_t *n_isects,        /* [1] device, from ubs_isect_count */
+                        int64_t capacity, int64_t *isect_ids, /* [capacity] sorted keys out */
+                        int32_t *flatten_ids,                 /* [capacity] sorted vals out */
+                        int32_t *offsets,                     /* [C,th,tw] or NULL */
+                        int32_t *status,                      /* [1] device or NULL */
+                        void *workspace, size_t workspace_bytes, void *stream);
+/* stand-alone offset encoding of already sorted keys (isect_tiles.cu:287-366). n_isects is a host value.     */
+int ubs_isect_offset_encode(int64_t n_isects, const int64_t *isect_ids, int C, int tile_width, int tile_height,
+                            int32_t *offsets, void *stream);
+/* stand-alone stable radix sort of (int64 key, int32 val) pairs on bits [begin_bit, end_bit); n on device.   */
+size_t ubs_radix_sort_workspace_bytes(int64_t capacity);
+int ubs_radix_sort_pairs(const int64_t *n_dev, int64_t capacity, int64_t *keys_in, int32_t *vals_in, int64_t *keys_out,
+                         int32_t *vals_out, int begin_bit, int end_bit, void *workspace, size_t workspace_bytes,
+                         void *stream);
+
+/* ---- K10/K11: per-tile alpha compositing with the Beta kernel ------------------------------------------ */
+/* replaces rasterize_to_pixels_{fwd,bwd}_tensor (bindings.h:201-252; rasterize_to_pixels_fwd.cu:16-191,
+ * rasterize_to_pixels_bwd.cu:16-276).  channels in [1, UBS_MAX_CHANNELS]; tile_size must be 16.
+ * n_isects is read from DEVICE memory (int64) so the call composes with the capacity-bounded sort.          */
+int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, const float *means2d, const float *conics,
+                      const float *colors,      /* [C,N,channels] */
+                      const float *opacities,   /* [C,N] */
+                      const float *betas,       /* [C,N] */
+                      const float *backgrounds, /* [C,channels] or NULL */
+                      const uint8_t *masks,     /* [C,th,tw] bool or NULL */
+                      int channels, int width, int height, int tile_size, const int32_t *offsets,
+                      const int32_t *flatten_ids, float *render_colors, /* [C,H,W,channels] */
+                      float *render_alphas,                             /* [C,H,W,1] */
+                      int32_t *last_ids,                                /* [C,H,W]   */
+                      void *stream);
+int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, const float *means2d, const float *conics,
+                      const float *colors, const float *opacities, const float *betas, const float *backgrounds,
+                      const uint8_t *masks, int channels, int width, int height, int tile_size, const int32_t *offsets,
+                      const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
+                      const float *v_render_colors, const float *v_render_alphas,
+                      /* gradients, ACCUMULATED into (caller zero-fills): */
+                      float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, float *v_betas,
+                      void *stream);
+
+/* ---- fused fast path: raw parameters -> screen-space records ------------------------------------------- */
+/* New entry (no single reference counterpart): fuses the activations (scene/beta_model.py:36-52,103-121),
+ * the view-direction / timestamp query (scene/beta_model.py:675-690), K1, K2, K3 and K5 in one pass over the
+ * PACKED primitive records, and the tile count of K7.  One launch covers all C cameras.
+ *
+ * Packed record (floats, row stride UBS_RECORD_STRIDE(D), 16-byte aligned rows):
+ *   [0,3) xyz | [3,D) mean | [D,D+3) rgb | D+3 opacity logit | [D+4, 2D+2) beta (D-2, raw) |
+ *   [2D+2, 3D+2) scale (raw, pre-softplus) | [3D+2, 3D+2+D(D-1)/2) l_triangle | zero padding to the stride
+ * D=6: 35 floats -> stride 36 (144 B).  D=7: 44 floats -> stride 44 (176 B).                                 */
+#define UBS_RECORD_FLOATS(D) (3 * (D) + 2 + (D) * ((D)-1) / 2)
+#define UBS_RECORD_STRIDE(D) ((UBS_RECORD_FLOATS(D) + 3) / 4 * 4)
+int ubs_record_stride(int D);
+
+int ubs_fused_project_fwd(int C, int64_t N, int D, const float *records, /* [N, stride] */
+                          const float *viewmats,                         /* [C,4,4] */
+                          const float *Ks,                               /* [C,3,3] */
+                          const float *cam_pos,                          /* [C,3] camera centres (world) */
+                          const float *timestamps,                       /* [C] (D=7) or NULL */
+                          const uint8_t *prim_mask,                      /* [N] bool or NULL (viewer filter) */
+                          int width, int height, float eps2d, float near_plane, float far_plane, float radius_clip,
+                          int calc_compensations, int tile_size, int tile_width, int tile_height,
+                          int32_t *radii,           /* [C,N]   */
+                          float *means2d,           /* [C,N,2] */
+                          float *depths,            /* [C,N]   */
+                          float *conics,            /* [C,N,3] */
+                          float *opacities,         /* [C,N] conditioned (x compensation if requested) */
+                          float *betas,             /* [C,N] spatial beta = 4 exp(raw beta_0) */
+                          float *colors,            /* [C,N,3] or NULL (rgb copied out of the record) */
+                          int32_t *tiles_per_gauss, /* [C,N] */
+                          int64_t *n_isects,        /* [1] device */
+                          void *workspace, size_t workspace_bytes, /* ubs_isect_workspace_bytes(C*N, cap) */
+                          void *stream);
+/* backward of the above: consumes gradients w.r.t. the screen-space records and writes a packed gradient
+ * record buffer (same layout as `records`; accumulated over cameras; zeroed by callee).                      */
+int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const float *viewmats, const float *Ks,
+                          const float *cam_pos, const float *timestamps, int width, int height, float eps2d,
+                          int calc_compensations, const int32_t *radii, const float *conics,
+                          const float *v_means2d, const float *v_depths, const float *v_conics,
+                          const float *v_opacities, const float *v_betas, const float *v_colors, /* [C,N,3] or NULL */
+                          float *v_records,                                                       /* [N, stride] */
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UBS_B200_H */

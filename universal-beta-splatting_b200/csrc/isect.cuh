@@ -1,0 +1,67 @@
+// Shared device helpers for tile intersection (used by isect.cu and the fused projection kernel).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ubs {
+
+constexpr int kIsectThreads = 256;
+
+struct TileRect {
+    uint32_t x0, y0, x1, y1;  // min inclusive, max exclusive
+};
+
+// Tile AABB of a projected primitive (isect_tiles.cu:56-66).  The float->uint32 casts of negative values
+// saturate to 0 (PTX cvt.rzi.u32.f32), which is what makes the reference's `max(0, (uint32_t)...)` work.
+__device__ __forceinline__ TileRect tile_rect(float mx, float my, int32_t radius_i, uint32_t tile_size,
+                                              uint32_t tile_width, uint32_t tile_height) {
+    const float radius = (float)radius_i;
+    const float tile_radius = radius / static_cast<float>(tile_size);
+    const float tile_x = mx / static_cast<float>(tile_size);
+    const float tile_y = my / static_cast<float>(tile_size);
+    TileRect t;
+    t.x0 = min(max(0u, (uint32_t)floorf(tile_x - tile_radius)), tile_width);
+    t.y0 = min(max(0u, (uint32_t)floorf(tile_y - tile_radius)), tile_height);
+    t.x1 = min(max(0u, (uint32_t)ceilf(tile_x + tile_radius)), tile_width);
+    t.y1 = min(max(0u, (uint32_t)ceilf(tile_y + tile_radius)), tile_height);
+    return t;
+}
+
+// Block-wide (kIsectThreads) int64 sum; result valid in thread 0.
+__device__ __forceinline__ int64_t block_reduce_sum_i64(int64_t v) {
+    __shared__ int64_t s_red[kIsectThreads / 32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    int64_t total = 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < kIsectThreads / 32; ++w) total += s_red[w];
+    }
+    return total;
+}
+
+// Block-wide (kIsectThreads) exclusive int64 scan.
+__device__ __forceinline__ int64_t block_exclusive_scan_i64(int64_t v) {
+    __shared__ int64_t s_scan[kIsectThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    int64_t base = 0;
+#pragma unroll
+    for (int w = 0; w < kIsectThreads / 32; ++w)
+        if (w < warp) base += s_scan[w];
+    return base + incl - v;
+}
+
+int isect_scan_and_total(int64_t n_blocks, int64_t *block_sums, int64_t *n_isects, cudaStream_t s);
+
+}  // namespace ubs

@@ -1,0 +1,173 @@
+// K10: per-tile front-to-back alpha compositing with the Beta falloff (forward).
+// Drop-in for rasterize_to_pixels_fwd (rasterize_to_pixels_fwd.cu:16-191): same sigma, alpha, early-termination
+// and last_ids semantics.  Differences in *how*: colours are staged through shared memory with the rest of the
+// 2-D record (the reference re-reads them from global memory per accepted pair), the gather of batch b+1 is
+// issued before batch b is composited (register double-buffering), and a warp whose 32 pixels are all done skips
+// the batch instead of spinning through it.
+#include "common.cuh"
+#include "raster_common.cuh"
+
+namespace ubs {
+
+namespace {
+
+template <int CH>
+__global__ void __launch_bounds__(kTilePixels)
+rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev, const float2 *__restrict__ means2d,
+                     const float *__restrict__ conics, const float *__restrict__ colors,
+                     const float *__restrict__ opacities, const float *__restrict__ betas,
+                     const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t width,
+                     uint32_t height, uint32_t tile_width, uint32_t tile_height,
+                     const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
+                     float *__restrict__ render_colors, float *__restrict__ render_alphas,
+                     int32_t *__restrict__ last_ids) {
+    const uint32_t cam = blockIdx.z;
+    const uint32_t tile_id = blockIdx.y * tile_width + blockIdx.x;
+    const uint32_t tr = threadIdx.y * kTile + threadIdx.x;
+    const uint32_t i = blockIdx.y * kTile + threadIdx.y;
+    const uint32_t j = blockIdx.x * kTile + threadIdx.x;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const bool inside = (i < height && j < width);
+    const size_t pix = ((size_t)cam * height + i) * width + j;
+
+    tile_offsets += (size_t)cam * tile_height * tile_width;
+    if (backgrounds != nullptr) backgrounds += cam * CH;
+
+    if (masks != nullptr && !masks[(size_t)cam * tile_height * tile_width + tile_id]) {
+        // masked-out tile: background colour only (rasterize_to_pixels_fwd.cu:73-79)
+        if (inside) {
+#pragma unroll
+            for (int k = 0; k < CH; ++k) render_colors[pix * CH + k] = backgrounds == nullptr ? 0.f : backgrounds[k];
+        }
+        return;
+    }
+
+    int64_t n_isects = *n_isects_dev;
+    const int32_t range_start = tile_offsets[tile_id];
+    const int32_t range_end = (cam == (uint32_t)C - 1 && tile_id == tile_width * tile_height - 1)
+                                  ? (int32_t)n_isects
+                                  : tile_offsets[tile_id + 1];
+    const int32_t n_pairs = range_end - range_start;
+    const int32_t num_batches = (n_pairs + kTilePixels - 1) / kTilePixels;
+
+    __shared__ float4 s_xyob[kTilePixels];      // mean2d.x, mean2d.y, opacity, beta
+    __shared__ float4 s_conic[kTilePixels];     // conic a, b, c, (unused)
+    __shared__ float s_color[kTilePixels * CH];
+
+    float T = 1.f;
+    int32_t cur_idx = 0;
+    bool done = !inside;
+    float pix_out[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) pix_out[k] = 0.f;
+
+    // register double buffer: the record this thread will publish for the next batch
+    float4 r_xyob = make_float4(0.f, 0.f, 0.f, 0.f), r_conic = r_xyob;
+    float r_color[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) r_color[k] = 0.f;
+    auto gather = [&](int32_t batch) {
+        const int32_t idx = range_start + batch * kTilePixels + (int32_t)tr;
+        if (idx < range_end) {
+            const int32_t g = flatten_ids[idx];
+            const float2 xy = means2d[g];
+            r_xyob = make_float4(xy.x, xy.y, opacities[g], betas[g]);
+            r_conic = make_float4(conics[(size_t)g * 3], conics[(size_t)g * 3 + 1], conics[(size_t)g * 3 + 2], 0.f);
+#pragma unroll
+            for (int k = 0; k < CH; ++k) r_color[k] = colors[(size_t)g * CH + k];
+        }
+    };
+    if (num_batches > 0) gather(0);
+
+    for (int32_t b = 0; b < num_batches; ++b) {
+        // everyone has finished reading the previous batch; stop when every pixel of the tile is done
+        if (__syncthreads_count(done) >= kTilePixels) break;
+        s_xyob[tr] = r_xyob;
+        s_conic[tr] = r_conic;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) s_color[tr * CH + k] = r_color[k];
+        __syncthreads();
+        if (b + 1 < num_batches) gather(b + 1);  // in flight while this batch is composited
+
+        const int32_t batch_start = range_start + b * kTilePixels;
+        const int32_t batch_size = min((int32_t)kTilePixels, range_end - batch_start);
+        if (__all_sync(0xffffffffu, done)) continue;  // whole warp finished: nothing to composite
+        for (int32_t t = 0; t < batch_size && !done; ++t) {
+            const float4 conic = s_conic[t];
+            const float4 xyob = s_xyob[t];
+            const float dx = xyob.x - px, dy = xyob.y - py;
+            const float sigma = (conic.x * dx * dx + conic.z * dy * dy) + 2.f * conic.y * dx * dy;
+            if (sigma < 0.f || sigma >= 1.f) continue;
+            const float alpha = fminf(0.999f, xyob.z * __powf(1.f - sigma, xyob.w));
+            const float next_T = T * (1.f - alpha);
+            if (next_T <= 1e-4f) {  // this pixel is done; the primitive is NOT accumulated
+                done = true;
+                break;
+            }
+            const float vis = alpha * T;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) pix_out[k] += s_color[t * CH + k] * vis;
+            cur_idx = batch_start + t;
+            T = next_T;
+        }
+    }
+
+    if (inside) {
+        render_alphas[pix] = 1.f - T;
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+            render_colors[pix * CH + k] = backgrounds == nullptr ? pix_out[k] : (pix_out[k] + T * backgrounds[k]);
+        last_ids[pix] = cur_idx;
+    }
+}
+
+template <int CH>
+int launch_fwd(int C, int64_t N, const int64_t *n_isects, const float *means2d, const float *conics,
+               const float *colors, const float *opacities, const float *betas, const float *backgrounds,
+               const uint8_t *masks, int width, int height, const int32_t *offsets, const int32_t *flatten_ids,
+               float *render_colors, float *render_alphas, int32_t *last_ids, cudaStream_t s) {
+    const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
+    dim3 grid(tw, th, (unsigned)C), block(kTile, kTile, 1);
+    rasterize_fwd_kernel<CH><<<grid, block, 0, s>>>(C, N, n_isects, (const float2 *)means2d, conics, colors, opacities,
+                                                    betas, backgrounds, masks, (uint32_t)width, (uint32_t)height, tw,
+                                                    th, offsets, flatten_ids, render_colors, render_alphas, last_ids);
+    UBS_LAUNCH_CHECK("rasterize_fwd_kernel");
+    return UBS_OK;
+}
+
+}  // namespace
+}  // namespace ubs
+
+extern "C" int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, const float *means2d, const float *conics,
+                                 const float *colors, const float *opacities, const float *betas,
+                                 const float *backgrounds, const uint8_t *masks, int channels, int width, int height,
+                                 int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
+                                 float *render_colors, float *render_alphas, int32_t *last_ids, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "rasterize_fwd: bad sizes");
+    UBS_CHECK_ARG(tile_size == kTile, "rasterize_fwd: tile_size must be %d (got %d)", kTile, tile_size);
+    if (C == 0) return UBS_OK;
+    UBS_CHECK_ARG(n_isects && offsets && render_colors && render_alphas && last_ids, "rasterize_fwd: null pointer");
+    UBS_CHECK_ARG(N == 0 || (means2d && conics && colors && opacities && betas && flatten_ids),
+                  "rasterize_fwd: null primitive arrays");
+    UBS_CHECK_ARG(C <= 65535, "rasterize_fwd: C=%d exceeds 65535", C);
+    cudaStream_t s = (cudaStream_t)stream;
+#define UBS_FWD_CASE(CH)                                                                                               \
+    case CH:                                                                                                           \
+        return launch_fwd<CH>(C, N, n_isects, means2d, conics, colors, opacities, betas, backgrounds, masks, width,    \
+                              height, offsets, flatten_ids, render_colors, render_alphas, last_ids, s);
+    switch (channels) {
+        UBS_FWD_CASE(1)
+        UBS_FWD_CASE(2)
+        UBS_FWD_CASE(3)
+        UBS_FWD_CASE(4)
+        UBS_FWD_CASE(8)
+        UBS_FWD_CASE(16)
+        UBS_FWD_CASE(32)
+        default:
+            set_error("rasterize_fwd: unsupported channel count %d (supported: 1,2,3,4,8,16,32; pad on the host)",
+                      channels);
+            return UBS_EUNSUPPORTED;
+    }
+#undef UBS_FWD_CASE
+}

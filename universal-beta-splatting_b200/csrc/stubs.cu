@@ -1,0 +1,30 @@
+// Entry points declared in ubs_b200.h whose kernels are not built yet return UBS_EUNSUPPORTED (loudly, never a
+// silent fallback).  Each stub disappears when its kernel file lands.
+#include "common.cuh"
+
+#define UBS_STUB(name, ...)                                                                                            \
+    extern "C" int name(__VA_ARGS__) {                                                                                 \
+        ubs::set_error(#name ": not implemented in this build");                                                       \
+        return UBS_EUNSUPPORTED;                                                                                       \
+    }
+
+UBS_STUB(ubs_l_triangle_to_rotmat_fwd, int64_t, const float *, float *, void *)
+UBS_STUB(ubs_l_triangle_to_rotmat_bwd, int64_t, const float *, float *, void *)
+UBS_STUB(ubs_rot_scale_l_triangle_to_covar_fwd, int64_t, int, int, const float *, const float *, const float *, float *,
+         void *)
+UBS_STUB(ubs_rot_scale_l_triangle_to_covar_bwd, int64_t, int, int, const float *, const float *, const float *,
+         const float *, float *, float *, float *, void *)
+UBS_STUB(ubs_cond_mean_covar_opacity_fwd, int64_t, int, const float *, const float *, const float *, const float *,
+         const float *, float *, float *, float *, void *)
+UBS_STUB(ubs_cond_mean_covar_opacity_bwd, int64_t, int, const float *, const float *, const float *, const float *,
+         const float *, const float *, const float *, const float *, float *, float *, float *, float *, void *)
+UBS_STUB(ubs_rasterize_bwd, int, int64_t, const int64_t *, const float *, const float *, const float *, const float *,
+         const float *, const float *, const uint8_t *, int, int, int, int, const int32_t *, const int32_t *,
+         const float *, const int32_t *, const float *, const float *, float *, float *, float *, float *, float *,
+         void *)
+UBS_STUB(ubs_fused_project_fwd, int, int64_t, int, const float *, const float *, const float *, const float *,
+         const float *, const uint8_t *, int, int, float, float, float, float, int, int, int, int, int32_t *, float *,
+         float *, float *, float *, float *, float *, int32_t *, int64_t *, void *, size_t, void *)
+UBS_STUB(ubs_fused_project_bwd, int, int64_t, int, const float *, const float *, const float *, const float *,
+         const float *, int, int, float, int, const int32_t *, const float *, const float *, const float *,
+         const float *, const float *, const float *, const float *, float *, void *)

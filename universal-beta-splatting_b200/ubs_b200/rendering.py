@@ -1,0 +1,133 @@
+"""rasterization(): the drop-in entry point behind which the B200 kernels sit.
+
+Signature, kwargs, return values and `meta` keys follow the reference exactly
+(submodules/gsplat/rendering.py:17-232), including its quirks: `l_triagnles` / `scales` are ignored when
+`covars` is given (the only way scene/beta_model.py:697-711 calls it), "EDepth" is not alpha-normalised
+(rendering.py:219 tests for "ED"), and background is zero for the depth-only modes.
+"""
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from .ops import fully_fused_projection, isect_tiles, rasterize_to_pixels
+
+RENDER_MODES = ["RGB", "Normal", "Diffuse", "Specular", "Depth", "EDepth", "RGB+D", "RGB+ED"]
+
+
+def depth_to_normal(depths: Tensor, camtoworlds: Tensor, Ks: Tensor) -> Tensor:
+    """z-depth map [..., H, W, 1] -> world-space normals [..., H, W, 3] by central differences of the
+    back-projected points; border pixels are zero (reference: submodules/gsplat/utils.py:40-131)."""
+    device = depths.device
+    height, width = depths.shape[-3:-1]
+    x, y = torch.meshgrid(torch.arange(width, device=device), torch.arange(height, device=device), indexing="xy")
+    fx, fy = Ks[..., 0, 0], Ks[..., 1, 1]
+    cx, cy = Ks[..., 0, 2], Ks[..., 1, 2]
+    dirs = torch.stack([(x - cx[..., None, None] + 0.5) / fx[..., None, None],
+                        (y - cy[..., None, None] + 0.5) / fy[..., None, None]], dim=-1)
+    dirs = F.pad(dirs, (0, 1), value=1.0)
+    dirs = torch.einsum("...ij,...hwj->...hwi", camtoworlds[..., :3, :3], dirs)
+    points = camtoworlds[..., :3, -1][..., None, None, :] + depths * dirs
+    dx = points[..., 2:, 1:-1, :] - points[..., :-2, 1:-1, :]
+    dy = points[..., 1:-1, 2:, :] - points[..., 1:-1, :-2, :]
+    normals = F.normalize(torch.cross(dx, dy, dim=-1), dim=-1)
+    return F.pad(normals, (0, 0, 1, 1, 1, 1), value=0.0)
+
+
+def rasterization(
+    means: Tensor,  # [N, 3]
+    l_triagnles: Tensor,  # ignored when covars is given
+    scales: Tensor,  # ignored when covars is given
+    opacities: Tensor,  # [N]
+    betas: Tensor,  # [N]
+    colors: Tensor,  # [(C,) N, D]
+    viewmats: Tensor,  # [C, 4, 4]
+    Ks: Tensor,  # [C, 3, 3]
+    width: int,
+    height: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: str = "RGB",
+    rasterize_mode: str = "classic",
+    channel_chunk: int = 32,
+    covars: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor, Dict]:
+    meta = {}
+    N = means.shape[0]
+    C = viewmats.shape[0]
+    assert means.shape == (N, 3), means.shape
+    if covars is None:
+        # The reference would need [N,4] quaternion-like `l_triagnles` here, a branch UBS never takes.
+        raise NotImplementedError("rasterization() requires `covars` (the only form the UBS caller uses)")
+    assert covars.shape == (N, 3, 3), covars.shape
+    tri = ([0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2])
+    covars6 = covars[..., tri[0], tri[1]]
+    assert opacities.shape == (N,), opacities.shape
+    assert betas.shape == (N,), betas.shape
+    assert viewmats.shape == (C, 4, 4), viewmats.shape
+    assert Ks.shape == (C, 3, 3), Ks.shape
+    assert render_mode in RENDER_MODES, render_mode
+    assert (colors.dim() == 2 and colors.shape[0] == N) or (
+        colors.dim() == 3 and colors.shape[:2] == (C, N)
+    ), colors.shape
+
+    radii, means2d, depths, conics, compensations = fully_fused_projection(
+        means, covars6, None, None, viewmats, Ks, width, height, eps2d=eps2d, near_plane=near_plane,
+        far_plane=far_plane, radius_clip=radius_clip, sparse_grad=False,
+        calc_compensations=(rasterize_mode == "antialiased"), ortho=False)
+    opacities = opacities.repeat(C, 1)  # [C, N]
+    betas = betas.repeat(C, 1)  # [C, N]
+    if compensations is not None:
+        opacities = opacities * compensations
+
+    meta.update({"camera_ids": None, "primitive_ids": None, "radii": radii, "means2d": means2d, "depths": depths,
+                 "conics": conics, "opacities": opacities, "betas": betas})
+
+    if colors.dim() == 2:
+        colors = colors.expand(C, -1, -1)
+    if render_mode in ["RGB+D", "RGB+ED"]:
+        colors = torch.cat((colors, depths[..., None]), dim=-1)
+        if backgrounds is not None:
+            backgrounds = torch.cat([backgrounds, torch.zeros(C, 1, device=backgrounds.device)], dim=-1)
+    elif render_mode in ["Depth", "EDepth", "Normal"]:
+        colors = depths[..., None]
+        if backgrounds is not None:
+            backgrounds = torch.zeros(C, 1, device=backgrounds.device)
+
+    tile_width = math.ceil(width / float(tile_size))
+    tile_height = math.ceil(height / float(tile_size))
+    tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_tiles(
+        means2d, radii, depths, tile_size, tile_width, tile_height, n_cameras=C, return_offsets=True)
+    meta.update({"tile_width": tile_width, "tile_height": tile_height, "tiles_per_gauss": tiles_per_gauss,
+                 "isect_ids": isect_ids, "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width,
+                 "height": height, "tile_size": tile_size, "n_cameras": C})
+
+    if colors.shape[-1] > channel_chunk:
+        n_chunks = (colors.shape[-1] + channel_chunk - 1) // channel_chunk
+        render_colors, render_alphas = [], []
+        for i in range(n_chunks):
+            sl = slice(i * channel_chunk, (i + 1) * channel_chunk)
+            rc, ra = rasterize_to_pixels(means2d, conics, colors[..., sl], opacities, betas, width, height, tile_size,
+                                         isect_offsets, flatten_ids,
+                                         backgrounds=backgrounds[..., sl] if backgrounds is not None else None)
+            render_colors.append(rc)
+            render_alphas.append(ra)
+        render_colors = torch.cat(render_colors, dim=-1)
+        render_alphas = render_alphas[0]
+    else:
+        render_colors, render_alphas = rasterize_to_pixels(means2d, conics, colors, opacities, betas, width, height,
+                                                           tile_size, isect_offsets, flatten_ids,
+                                                           backgrounds=backgrounds)
+    if render_mode in ["ED", "RGB+ED"]:
+        render_colors = torch.cat(
+            [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
+    if render_mode == "Normal":
+        render_colors = depth_to_normal(render_colors, torch.inverse(viewmats), Ks)
+        render_colors = (render_colors + 1) / 2
+    return render_colors, render_alphas, meta
