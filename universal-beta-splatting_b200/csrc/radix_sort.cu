@@ -281,6 +281,7 @@ extern "C" int ubs_radix_sort_pairs(const int64_t *n_dev, int64_t capacity, int6
                                     int64_t *keys_out, int32_t *vals_out, int begin_bit, int end_bit, void *workspace,
                                     size_t workspace_bytes, void *stream) {
     using namespace ubs;
+    if (capacity == 0) return UBS_OK;
     UBS_CHECK_ARG(n_dev && keys_in && vals_in && keys_out && vals_out && workspace, "radix_sort_pairs: null pointer");
     if (workspace_bytes < sort_workspace_bytes(capacity)) {
         set_error("radix_sort_pairs: workspace %zu < %zu", workspace_bytes, sort_workspace_bytes(capacity));

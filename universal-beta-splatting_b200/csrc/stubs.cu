@@ -8,16 +8,6 @@
         return UBS_EUNSUPPORTED;                                                                                       \
     }
 
-UBS_STUB(ubs_l_triangle_to_rotmat_fwd, int64_t, const float *, float *, void *)
-UBS_STUB(ubs_l_triangle_to_rotmat_bwd, int64_t, const float *, float *, void *)
-UBS_STUB(ubs_rot_scale_l_triangle_to_covar_fwd, int64_t, int, int, const float *, const float *, const float *, float *,
-         void *)
-UBS_STUB(ubs_rot_scale_l_triangle_to_covar_bwd, int64_t, int, int, const float *, const float *, const float *,
-         const float *, float *, float *, float *, void *)
-UBS_STUB(ubs_cond_mean_covar_opacity_fwd, int64_t, int, const float *, const float *, const float *, const float *,
-         const float *, float *, float *, float *, void *)
-UBS_STUB(ubs_cond_mean_covar_opacity_bwd, int64_t, int, const float *, const float *, const float *, const float *,
-         const float *, const float *, const float *, const float *, float *, float *, float *, float *, void *)
 UBS_STUB(ubs_rasterize_bwd, int, int64_t, const int64_t *, const float *, const float *, const float *, const float *,
          const float *, const float *, const uint8_t *, int, int, int, int, const int32_t *, const int32_t *,
          const float *, const int32_t *, const float *, const float *, float *, float *, float *, float *, float *,

@@ -336,3 +336,132 @@ def rasterize_to_pixels(
     if padded_channels > 0:
         render_colors = render_colors[..., :-padded_channels]
     return render_colors, render_alphas
+
+
+# --------------------------------------------------------------------------------------------------------------
+# K1-K4: covariance build and conditioning (companion operators of scene/beta_model.py:12-22)
+# --------------------------------------------------------------------------------------------------------------
+class _LTriangleToRotmat(torch.autograd.Function):
+    """Mirror of cuda/_wrapper.py:614-630."""
+
+    @staticmethod
+    def forward(ctx, l_triangle):
+        lib = _lib.load()
+        N = l_triangle.shape[0]
+        rot = torch.empty((N, 3, 3), dtype=torch.float32, device=l_triangle.device)
+        check(lib.ubs_l_triangle_to_rotmat_fwd(N, ptr(l_triangle), ptr(rot), _stream()), "ubs_l_triangle_to_rotmat_fwd")
+        return rot
+
+    @staticmethod
+    def backward(ctx, v_rot):
+        lib = _lib.load()
+        v_rot = _req(v_rot, "v_rot")
+        N = v_rot.shape[0]
+        v_lt = torch.empty((N, 3), dtype=torch.float32, device=v_rot.device)
+        check(lib.ubs_l_triangle_to_rotmat_bwd(N, ptr(v_rot), ptr(v_lt), _stream()), "ubs_l_triangle_to_rotmat_bwd")
+        return v_lt
+
+
+def l_triangle_to_rotmat(l_triangle: Tensor) -> Tensor:
+    """[N,3] skew parameters -> [N,3,3] first-order rotation I + A (cuda/_wrapper.py:34-36)."""
+    assert l_triangle.shape[1] == 3, l_triangle.shape
+    return _LTriangleToRotmat.apply(_req(l_triangle, "l_triangle"))
+
+
+def _check_rest_layout(D: int, rest_i: Tensor, rest_j: Tensor):
+    """The kernels hard-wire torch.tril_indices(D, D, -1) order; reject anything else loudly."""
+    ti, tj = torch.tril_indices(D, D, offset=-1)
+    m = (ti >= 3) | (tj >= 3)
+    if rest_i.numel() != int(m.sum()) or not torch.equal(rest_i.cpu().long(), ti[m]) or not torch.equal(
+            rest_j.cpu().long(), tj[m]):
+        raise NotImplementedError("rest_i/rest_j must be the tril_indices layout built by scene/beta_model.py:69-73")
+
+
+_REST_OK = set()
+
+
+class _RotScaleLTriangleToCovar(torch.autograd.Function):
+    """Mirror of cuda/_wrapper.py:633-684."""
+
+    @staticmethod
+    def forward(ctx, rot, scale, l_triangle, spatial_block):
+        lib = _lib.load()
+        N, D = scale.shape
+        d = 3 if (spatial_block or D == 3) else D
+        covar = torch.empty((N, d, d), dtype=torch.float32, device=scale.device)
+        check(lib.ubs_rot_scale_l_triangle_to_covar_fwd(N, D, 1 if d == 3 else 0, ptr(rot), ptr(scale),
+                                                        ptr(l_triangle), ptr(covar), _stream()),
+              "ubs_rot_scale_l_triangle_to_covar_fwd")
+        ctx.save_for_backward(rot, scale, l_triangle)
+        ctx.spatial = d == 3
+        return covar
+
+    @staticmethod
+    def backward(ctx, v_covar):
+        rot, scale, l_triangle = ctx.saved_tensors
+        if not any(ctx.needs_input_grad[:3]):
+            return None, None, None, None
+        lib = _lib.load()
+        N, D = scale.shape
+        v_rot, v_scale, v_lt = torch.empty_like(rot), torch.empty_like(scale), torch.empty_like(l_triangle)
+        check(lib.ubs_rot_scale_l_triangle_to_covar_bwd(N, D, 1 if ctx.spatial else 0, ptr(rot), ptr(scale),
+                                                        ptr(l_triangle), ptr(_req(v_covar, "v_covar")), ptr(v_rot),
+                                                        ptr(v_scale), ptr(v_lt), _stream()),
+              "ubs_rot_scale_l_triangle_to_covar_bwd")
+        return v_rot, v_scale, v_lt, None
+
+
+def rot_scale_l_triangle_to_covar(rot: Tensor, scale: Tensor, l_triangle: Tensor, rest_i: Tensor, rest_j: Tensor,
+                                  spatial_block: bool = False) -> Tensor:
+    """Sigma = L L^T (cuda/_wrapper.py:39-55).  D in [4, 8]."""
+    D = scale.shape[1]
+    key = (D, rest_i.data_ptr(), rest_j.data_ptr())
+    if key not in _REST_OK:  # validated once per index tensor (needs a host copy)
+        _check_rest_layout(D, rest_i, rest_j)
+        _REST_OK.add(key)
+    assert rot.shape[1:] == (3, 3) and l_triangle.shape[1] == D * (D - 1) // 2
+    return _RotScaleLTriangleToCovar.apply(_req(rot, "rot"), _req(scale, "scale"), _req(l_triangle, "l_triangle"),
+                                           bool(spatial_block))
+
+
+class _CondMeanConvarianceOpacity(torch.autograd.Function):
+    """Mirror of cuda/_wrapper.py:573-611 (no gradient for `query`)."""
+
+    @staticmethod
+    def forward(ctx, means, covars, opacities, betas, query):
+        lib = _lib.load()
+        N, D = means.shape
+        dev = means.device
+        om = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        oc = torch.empty((N, 3, 3), dtype=torch.float32, device=dev)
+        oo = torch.empty((N, 1), dtype=torch.float32, device=dev)
+        check(lib.ubs_cond_mean_covar_opacity_fwd(N, D, ptr(means), ptr(covars), ptr(opacities), ptr(betas),
+                                                  ptr(query), ptr(om), ptr(oc), ptr(oo), _stream()),
+              "ubs_cond_mean_covar_opacity_fwd")
+        ctx.save_for_backward(means, covars, opacities, betas, query)
+        return om, oc, oo
+
+    @staticmethod
+    def backward(ctx, v_om, v_oc, v_oo):
+        means, covars, opacities, betas, query = ctx.saved_tensors
+        lib = _lib.load()
+        N, D = means.shape
+        v_means, v_covars = torch.empty_like(means), torch.empty_like(covars)
+        v_opac, v_betas = torch.empty_like(opacities), torch.empty_like(betas)
+        check(lib.ubs_cond_mean_covar_opacity_bwd(N, D, ptr(means), ptr(covars), ptr(opacities), ptr(betas),
+                                                  ptr(query), ptr(_req(v_om, "v_means")), ptr(_req(v_oc, "v_covars")),
+                                                  ptr(_req(v_oo, "v_opacities")), ptr(v_means), ptr(v_covars),
+                                                  ptr(v_opac), ptr(v_betas), _stream()),
+              "ubs_cond_mean_covar_opacity_bwd")
+        return v_means, v_covars, v_opac, v_betas, None
+
+
+def cond_mean_convariance_opacity(means: Tensor, covars: Tensor, opacities: Tensor, betas: Tensor,
+                                  query: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """Condition the D-dim primitive on `query` (cuda/_wrapper.py:18-31).  means [N,D], covars [N,D,D],
+    opacities [N,1], betas/query [N,D-3] -> means [N,3], covars [N,3,3], opacities [N,1]."""
+    N, D = means.shape
+    assert covars.shape == (N, D, D) and opacities.shape == (N, 1)
+    assert betas.shape == (N, D - 3) and query.shape == (N, D - 3)
+    return _CondMeanConvarianceOpacity.apply(_req(means, "means"), _req(covars, "covars"),
+                                             _req(opacities, "opacities"), _req(betas, "betas"), _req(query, "query"))
