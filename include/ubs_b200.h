@@ -146,8 +146,10 @@ int ubs_radix_sort_pairs(const int64_t *n_dev, int64_t capacity, int64_t *keys_i
 /* ---- K10/K11: per-tile alpha compositing with the Beta kernel ------------------------------------------ */
 /* replaces rasterize_to_pixels_{fwd,bwd}_tensor (bindings.h:201-252; rasterize_to_pixels_fwd.cu:16-191,
  * rasterize_to_pixels_bwd.cu:16-276).  channels in [1, UBS_MAX_CHANNELS]; tile_size must be 16.
- * n_isects is read from DEVICE memory (int64) so the call composes with the capacity-bounded sort.          */
-int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, const float *means2d, const float *conics,
+ * n_isects is read from DEVICE memory (int64) so the call composes with the capacity-bounded sort; it is clamped
+ * to isect_capacity (the number of elements of flatten_ids) inside the kernels.                               */
+int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity, const float *means2d,
+                      const float *conics,
                       const float *colors,      /* [C,N,channels] */
                       const float *opacities,   /* [C,N] */
                       const float *betas,       /* [C,N] */
@@ -158,7 +160,8 @@ int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, const float *me
                       float *render_alphas,                             /* [C,H,W,1] */
                       int32_t *last_ids,                                /* [C,H,W]   */
                       void *stream);
-int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, const float *means2d, const float *conics,
+int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity, const float *means2d,
+                      const float *conics,
                       const float *colors, const float *opacities, const float *betas, const float *backgrounds,
                       const uint8_t *masks, int channels, int width, int height, int tile_size, const int32_t *offsets,
                       const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,

@@ -262,12 +262,18 @@ struct CondOut {
     float opacity;
 };
 
-// mu1[3], x = q - mu2 [C], V11[9], V12[3*C], V21[C*3], V22[C*C], o, beta[C]
+// Camera-independent part of the conditioning: everything except x = q - mu2.  With many cameras per launch the
+// inverse, the regression matrix, the conditional covariance and the Cholesky factor are computed once.
 template <int C>
-__device__ __forceinline__ CondOut<C> cond_forward(const float mu1[3], const float x[C], const float V11[9],
-                                                   const float V12[3 * C], const float V21[C * 3],
-                                                   const float V22[C * C], float o_in, const float beta[C]) {
-    CondOut<C> out;
+struct CondPrep {
+    float rb[3 * C];   // V12 V22^-1 diag(beta_adj)
+    float cov[9];      // V11 - rb V21 (full 3x3, not symmetrised, as the reference)
+    float Lc[C * C];   // guarded Cholesky factor of V22
+};
+
+template <int C>
+__device__ __forceinline__ void cond_prepare(const float V11[9], const float V12[3 * C], const float V21[C * 3],
+                                             const float V22[C * C], const float beta[C], CondPrep<C> &p) {
     float beta_adj[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
@@ -276,7 +282,6 @@ __device__ __forceinline__ CondOut<C> cond_forward(const float mu1[3], const flo
     }
     float i22[C * C];
     invert_small<C>(V22, i22);
-    float rb[3 * C];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -284,36 +289,40 @@ __device__ __forceinline__ CondOut<C> cond_forward(const float mu1[3], const flo
             float acc = 0.f;
 #pragma unroll
             for (int k = 0; k < C; ++k) acc += V12[r * C + k] * i22[k * C + c];
-            rb[r * C + c] = acc * beta_adj[c];
+            p.rb[r * C + c] = acc * beta_adj[c];
         }
-    float mc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        mc[0] += rb[0 * C + c] * x[c];
-        mc[1] += rb[1 * C + c] * x[c];
-        mc[2] += rb[2 * C + c] * x[c];
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) out.mean[r] = mu1[r] + mc[r];
     float vc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < C; ++k)
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) vc[r * 3 + c] += rb[r * C + k] * V21[k * 3 + c];
+            for (int c = 0; c < 3; ++c) vc[r * 3 + c] += p.rb[r * C + k] * V21[k * 3 + c];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) out.cov[i] = V11[i] - vc[i];
+    for (int i = 0; i < 9; ++i) p.cov[i] = V11[i] - vc[i];
+    cholesky_guarded<C>(V22, p.Lc);
+}
 
-    float Lc[C * C];
-    cholesky_guarded<C>(V22, Lc);
+// Camera-dependent part: conditional mean and opacity for x = q - mu2.
+template <int C>
+__device__ __forceinline__ void cond_apply(const CondPrep<C> &p, const float mu1[3], const float x[C], float o_in,
+                                           const float beta[C], float mean[3], float &opacity) {
+    float mc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        mc[0] += p.rb[0 * C + c] * x[c];
+        mc[1] += p.rb[1 * C + c] * x[c];
+        mc[2] += p.rb[2 * C + c] * x[c];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) mean[r] = mu1[r] + mc[r];
     float y[C];
 #pragma unroll
     for (int i = 0; i < C; ++i) {
         float sum = x[i];
 #pragma unroll
-        for (int k = 0; k < i; ++k) sum -= Lc[i * C + k] * y[k];
-        y[i] = sum / guard_denom(Lc[i * C + i]);
+        for (int k = 0; k < i; ++k) sum -= p.Lc[i * C + k] * y[k];
+        y[i] = sum / guard_denom(p.Lc[i * C + i]);
     }
     float o_change = 1.f;
     const float upper = 1.f - FLT_EPSILON;
@@ -324,7 +333,20 @@ __device__ __forceinline__ CondOut<C> cond_forward(const float mu1[3], const flo
         if (d > upper) d = upper;
         o_change *= powf(1.f - d, beta[i]);
     }
-    out.opacity = o_in * o_change;
+    opacity = o_in * o_change;
+}
+
+// mu1[3], x = q - mu2 [C], V11[9], V12[3*C], V21[C*3], V22[C*C], o, beta[C]
+template <int C>
+__device__ __forceinline__ CondOut<C> cond_forward(const float mu1[3], const float x[C], const float V11[9],
+                                                   const float V12[3 * C], const float V21[C * 3],
+                                                   const float V22[C * C], float o_in, const float beta[C]) {
+    CondOut<C> out;
+    CondPrep<C> p;
+    cond_prepare<C>(V11, V12, V21, V22, beta, p);
+    cond_apply<C>(p, mu1, x, o_in, beta, out.mean, out.opacity);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) out.cov[i] = p.cov[i];
     return out;
 }
 

@@ -29,6 +29,14 @@ isect_count_kernel(int64_t CN, const float *__restrict__ means2d, const int32_t 
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
+// phase 1 variant for the fused projection kernel, which already wrote the per-primitive tile counts
+__global__ void __launch_bounds__(kIsectThreads)
+isect_blocksum_kernel(int64_t CN, const int32_t *__restrict__ tiles_per_gauss, int64_t *__restrict__ block_sums) {
+    const int64_t idx = (int64_t)blockIdx.x * kIsectThreads + threadIdx.x;
+    const int64_t total = block_reduce_sum_i64(idx < CN ? (int64_t)tiles_per_gauss[idx] : 0);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
 // ---- phase 3: emit pairs; block-local exclusive scan of the counts + scanned block base ---------------------
 __global__ void __launch_bounds__(kIsectThreads)
 isect_emit_kernel(int64_t CN, int64_t N, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
@@ -150,6 +158,14 @@ IsectWorkspace carve(void *base, int64_t CN) {
 }
 
 }  // namespace
+
+int isect_blocksums_from_counts(int64_t CN, const int32_t *tiles_per_gauss, void *workspace, int64_t *n_isects,
+                                cudaStream_t s) {
+    IsectWorkspace w = carve(workspace, CN);
+    isect_blocksum_kernel<<<(unsigned)w.n_blocks, kIsectThreads, 0, s>>>(CN, tiles_per_gauss, w.block_sums);
+    UBS_LAUNCH_CHECK("isect_blocksum_kernel");
+    return isect_scan_and_total(w.n_blocks, w.block_sums, n_isects, s);
+}
 
 int isect_scan_and_total(int64_t n_blocks, int64_t *block_sums, int64_t *n_isects, cudaStream_t s) {
     isect_scan_blocks_kernel<<<1, 1024, 0, s>>>(n_blocks, block_sums, n_isects);

@@ -63,5 +63,9 @@ __device__ __forceinline__ int64_t block_exclusive_scan_i64(int64_t v) {
 }
 
 int isect_scan_and_total(int64_t n_blocks, int64_t *block_sums, int64_t *n_isects, cudaStream_t s);
+// block sums + scan + total from already computed per-(camera, primitive) tile counts; `workspace` is the buffer
+// later handed to ubs_isect_emit_sort.
+int isect_blocksums_from_counts(int64_t CN, const int32_t *tiles_per_gauss, void *workspace, int64_t *n_isects,
+                                cudaStream_t s);
 
 }  // namespace ubs

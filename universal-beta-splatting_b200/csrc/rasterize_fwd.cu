@@ -13,7 +13,8 @@ namespace {
 
 template <int CH>
 __global__ void __launch_bounds__(kTilePixels)
-rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev, const float2 *__restrict__ means2d,
+rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev, int64_t isect_capacity,
+                     const float2 *__restrict__ means2d,
                      const float *__restrict__ conics, const float *__restrict__ colors,
                      const float *__restrict__ opacities, const float *__restrict__ betas,
                      const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t width,
@@ -42,7 +43,7 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         return;
     }
 
-    int64_t n_isects = *n_isects_dev;
+    const int64_t n_isects = min(*n_isects_dev, isect_capacity);
     const int32_t range_start = tile_offsets[tile_id];
     const int32_t range_end = (cam == (uint32_t)C - 1 && tile_id == tile_width * tile_height - 1)
                                   ? (int32_t)n_isects
@@ -122,13 +123,13 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
 }
 
 template <int CH>
-int launch_fwd(int C, int64_t N, const int64_t *n_isects, const float *means2d, const float *conics,
+int launch_fwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const float *means2d, const float *conics,
                const float *colors, const float *opacities, const float *betas, const float *backgrounds,
                const uint8_t *masks, int width, int height, const int32_t *offsets, const int32_t *flatten_ids,
                float *render_colors, float *render_alphas, int32_t *last_ids, cudaStream_t s) {
     const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
     dim3 grid(tw, th, (unsigned)C), block(kTile, kTile, 1);
-    rasterize_fwd_kernel<CH><<<grid, block, 0, s>>>(C, N, n_isects, (const float2 *)means2d, conics, colors, opacities,
+    rasterize_fwd_kernel<CH><<<grid, block, 0, s>>>(C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities,
                                                     betas, backgrounds, masks, (uint32_t)width, (uint32_t)height, tw,
                                                     th, offsets, flatten_ids, render_colors, render_alphas, last_ids);
     UBS_LAUNCH_CHECK("rasterize_fwd_kernel");
@@ -138,7 +139,8 @@ int launch_fwd(int C, int64_t N, const int64_t *n_isects, const float *means2d, 
 }  // namespace
 }  // namespace ubs
 
-extern "C" int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, const float *means2d, const float *conics,
+extern "C" int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
+                                 const float *means2d, const float *conics,
                                  const float *colors, const float *opacities, const float *betas,
                                  const float *backgrounds, const uint8_t *masks, int channels, int width, int height,
                                  int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
@@ -154,7 +156,7 @@ extern "C" int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, cons
     cudaStream_t s = (cudaStream_t)stream;
 #define UBS_FWD_CASE(CH)                                                                                               \
     case CH:                                                                                                           \
-        return launch_fwd<CH>(C, N, n_isects, means2d, conics, colors, opacities, betas, backgrounds, masks, width,    \
+        return launch_fwd<CH>(C, N, n_isects, isect_capacity, means2d, conics, colors, opacities, betas, backgrounds, masks, width,    \
                               height, offsets, flatten_ids, render_colors, render_alphas, last_ids, s);
     switch (channels) {
         UBS_FWD_CASE(1)

@@ -8,13 +8,10 @@
         return UBS_EUNSUPPORTED;                                                                                       \
     }
 
-UBS_STUB(ubs_rasterize_bwd, int, int64_t, const int64_t *, const float *, const float *, const float *, const float *,
+UBS_STUB(ubs_rasterize_bwd, int, int64_t, const int64_t *, int64_t, const float *, const float *, const float *, const float *,
          const float *, const float *, const uint8_t *, int, int, int, int, const int32_t *, const int32_t *,
          const float *, const int32_t *, const float *, const float *, float *, float *, float *, float *, float *,
          void *)
-UBS_STUB(ubs_fused_project_fwd, int, int64_t, int, const float *, const float *, const float *, const float *,
-         const float *, const uint8_t *, int, int, float, float, float, float, int, int, int, int, int32_t *, float *,
-         float *, float *, float *, float *, float *, int32_t *, int64_t *, void *, size_t, void *)
 UBS_STUB(ubs_fused_project_bwd, int, int64_t, int, const float *, const float *, const float *, const float *,
          const float *, int, int, float, int, const int32_t *, const float *, const float *, const float *,
          const float *, const float *, const float *, const float *, float *, void *)

@@ -34,9 +34,9 @@ SIGNATURES = {
     "ubs_isect_offset_encode": (c_int, [c_int64, _P, c_int, c_int, c_int, _P, _P]),
     "ubs_radix_sort_workspace_bytes": (c_size_t, [c_int64]),
     "ubs_radix_sort_pairs": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int, c_int, _P, c_size_t, _P]),
-    "ubs_rasterize_fwd": (c_int, [c_int, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
+    "ubs_rasterize_fwd": (c_int, [c_int, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
                                   _P, _P, _P, _P]),
-    "ubs_rasterize_bwd": (c_int, [c_int, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int] +
+    "ubs_rasterize_bwd": (c_int, [c_int, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int] +
                           [_P] * 12),
     "ubs_fused_project_fwd": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_float,
                                       c_float, c_float, c_int, c_int, c_int, c_int] + [_P] * 10 + [c_size_t, _P]),

@@ -1,0 +1,146 @@
+"""Fused fast path: packed primitive records + cameras -> image (and back), with zero host synchronisation.
+
+This is the B200-first restructuring of `BetaModel.render` (scene/beta_model.py:660-722): the seven raw parameter
+tensors live in ONE packed [N, stride] FP32 buffer (layout in include/ubs_b200.h), one kernel does the
+activations + covariance build + conditioning + projection + tile count for all cameras, the pair list is
+capacity-bounded so its length never has to visit the host, and all scratch is allocated once and reused.
+"""
+import math
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def record_stride(D: int) -> int:
+    return (3 * D + 2 + D * (D - 1) // 2 + 3) // 4 * 4
+
+
+def record_slices(D: int):
+    """Column ranges of the packed record (must match include/ubs_b200.h)."""
+    o = 0
+    out = {}
+    for name, w in (("xyz", 3), ("mean", D - 3), ("rgb", 3), ("opacity", 1), ("beta", D - 2), ("scale", D),
+                    ("l_triangle", D * (D - 1) // 2)):
+        out[name] = slice(o, o + w)
+        o += w
+    return out
+
+
+def pack_records(D, xyz, mean, rgb, opacity, beta, scale, l_triangle) -> Tensor:
+    """7 raw BetaModel tensors (scene/beta_model.py:57-63) -> packed [N, stride] records (zero padded)."""
+    N = xyz.shape[0]
+    rec = torch.zeros((N, record_stride(D)), dtype=torch.float32, device=xyz.device)
+    sl = record_slices(D)
+    for name, t in (("xyz", xyz), ("mean", mean), ("rgb", rgb), ("opacity", opacity.reshape(N, 1)), ("beta", beta),
+                    ("scale", scale), ("l_triangle", l_triangle)):
+        rec[:, sl[name]] = t
+    return rec
+
+
+def unpack_records(D, rec: Tensor):
+    """Views into the packed buffer, in BetaModel order (xyz, mean, rgb, opacity, beta, scale, l_triangle)."""
+    sl = record_slices(D)
+    return tuple(rec[:, sl[n]] for n in ("xyz", "mean", "rgb", "opacity", "beta", "scale", "l_triangle"))
+
+
+class FusedRasterizer:
+    """Persistent buffers + the launch sequence fused-project -> emit/sort/offsets -> composite.
+
+    `capacity` bounds the number of (primitive, tile) pairs.  It grows automatically: the pair count of every
+    frame is copied to pinned host memory asynchronously and inspected (without blocking) on the next call.
+    `overflowed()` tells whether the most recent completed frame was truncated.
+    """
+
+    def __init__(self, D: int, N: int, width: int, height: int, n_cams: int = 1, capacity: Optional[int] = None,
+                 tile_size: int = 16, device="cuda", eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0,
+                 antialiased=False):
+        self.lib = _lib.load()
+        self.D, self.N, self.W, self.H, self.C = D, N, width, height, n_cams
+        self.tile_size = tile_size
+        self.tw, self.th = math.ceil(width / tile_size), math.ceil(height / tile_size)
+        self.eps2d, self.near, self.far, self.clip, self.aa = eps2d, near_plane, far_plane, radius_clip, antialiased
+        self.device = torch.device(device)
+        dev = self.device
+        C = n_cams
+        f32, i32 = torch.float32, torch.int32
+        self.radii = torch.empty((C, N), dtype=i32, device=dev)
+        self.means2d = torch.empty((C, N, 2), dtype=f32, device=dev)
+        self.depths = torch.empty((C, N), dtype=f32, device=dev)
+        self.conics = torch.empty((C, N, 3), dtype=f32, device=dev)
+        self.opacities = torch.empty((C, N), dtype=f32, device=dev)
+        self.betas = torch.empty((C, N), dtype=f32, device=dev)
+        self.colors = torch.empty((C, N, 3), dtype=f32, device=dev)
+        self.tiles_per_gauss = torch.empty((C, N), dtype=i32, device=dev)
+        self.n_isects = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.status = torch.zeros((1,), dtype=i32, device=dev)
+        self.offsets = torch.empty((C, self.th, self.tw), dtype=i32, device=dev)
+        self.render_colors = torch.empty((C, height, width, 3), dtype=f32, device=dev)
+        self.render_alphas = torch.empty((C, height, width, 1), dtype=f32, device=dev)
+        self.last_ids = torch.empty((C, height, width), dtype=i32, device=dev)
+        self._host_count = torch.zeros((2,), dtype=torch.int64).pin_memory()
+        self._count_event = None
+        self._alloc_pairs(capacity if capacity is not None else max(8 * C * N, 1 << 16))
+        self.launches_per_frame = 0
+
+    def _alloc_pairs(self, capacity: int):
+        self.capacity = int(capacity)
+        dev = self.device
+        self.isect_ids = torch.empty((self.capacity,), dtype=torch.int64, device=dev)
+        self.flatten_ids = torch.empty((self.capacity,), dtype=torch.int32, device=dev)
+        nbytes = self.lib.ubs_isect_workspace_bytes(self.C * self.N, self.capacity)
+        self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+
+    def _poll_count(self):
+        """Non-blocking look at the previous frame's pair count; grows the pair buffers when needed."""
+        if self._count_event is not None and self._count_event.query():
+            n = int(self._host_count[0])
+            self._count_event = None
+            if n > self.capacity:
+                self._alloc_pairs(int(n * 1.25) + 1024)
+                self.status.zero_()
+
+    def last_pair_count(self) -> int:
+        """Blocking read of the last frame's pair count (diagnostics / tests)."""
+        return int(self.n_isects.item())
+
+    def overflowed(self) -> bool:
+        return bool(self.status.item() & 1)
+
+    @torch.no_grad()
+    def forward(self, records: Tensor, viewmats: Tensor, Ks: Tensor, cam_pos: Tensor,
+                timestamps: Optional[Tensor] = None, backgrounds: Optional[Tensor] = None,
+                prim_mask: Optional[Tensor] = None):
+        """records [N,stride], viewmats [C,4,4], Ks [C,3,3], cam_pos [C,3], timestamps [C] (D=7),
+        backgrounds [C,3] -> (render_colors [C,H,W,3], render_alphas [C,H,W,1]) (buffers owned by self)."""
+        lib, s = self.lib, torch.cuda.current_stream().cuda_stream
+        C, N, D = self.C, self.N, self.D
+        assert records.shape == (N, record_stride(D)) and records.is_cuda and records.dtype == torch.float32
+        assert records.is_contiguous()
+        assert viewmats.shape == (C, 4, 4) and Ks.shape == (C, 3, 3) and cam_pos.shape == (C, 3)
+        self._poll_count()
+        mask_u8 = None if prim_mask is None else prim_mask.to(torch.bool).contiguous().view(torch.uint8)
+        check(lib.ubs_fused_project_fwd(
+            C, N, D, ptr(records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), ptr(mask_u8), self.W, self.H,
+            self.eps2d, self.near, self.far, self.clip, 1 if self.aa else 0, self.tile_size, self.tw, self.th,
+            ptr(self.radii), ptr(self.means2d), ptr(self.depths), ptr(self.conics), ptr(self.opacities),
+            ptr(self.betas), ptr(self.colors), ptr(self.tiles_per_gauss), ptr(self.n_isects), ptr(self.workspace),
+            self.workspace.numel(), s), "ubs_fused_project_fwd")
+        check(lib.ubs_isect_emit_sort(
+            C, N, ptr(self.means2d), ptr(self.radii), ptr(self.depths), self.tile_size, self.tw, self.th, 1,
+            ptr(self.tiles_per_gauss), ptr(self.n_isects), self.capacity, ptr(self.isect_ids), ptr(self.flatten_ids),
+            ptr(self.offsets), ptr(self.status), ptr(self.workspace), self.workspace.numel(), s), "ubs_isect_emit_sort")
+        check(lib.ubs_rasterize_fwd(
+            C, N, ptr(self.n_isects), self.capacity, ptr(self.means2d), ptr(self.conics), ptr(self.colors),
+            ptr(self.opacities),
+            ptr(self.betas), ptr(backgrounds), None, 3, self.W, self.H, self.tile_size, ptr(self.offsets),
+            ptr(self.flatten_ids), ptr(self.render_colors), ptr(self.render_alphas), ptr(self.last_ids), s),
+            "ubs_rasterize_fwd")
+        if self._count_event is None:
+            self._host_count[0:1].copy_(self.n_isects, non_blocking=True)
+            self._count_event = torch.cuda.Event()
+            self._count_event.record()
+        return self.render_colors, self.render_alphas

@@ -219,7 +219,7 @@ def rasterize_fwd(means2d, conics, colors, opacities, betas, backgrounds, masks,
     render_colors = torch.empty((C, height, width, ch), dtype=torch.float32, device=dev)
     render_alphas = torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
     last_ids = torch.empty((C, height, width), dtype=torch.int32, device=dev)
-    check(lib.ubs_rasterize_fwd(C, N, ptr(n_isects_dev), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
+    check(lib.ubs_rasterize_fwd(C, N, ptr(n_isects_dev), flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
                                 ptr(betas), ptr(backgrounds), ptr(masks), ch, int(width), int(height), int(tile_size),
                                 ptr(isect_offsets), ptr(flatten_ids), ptr(render_colors), ptr(render_alphas),
                                 ptr(last_ids), _stream()),
@@ -241,7 +241,7 @@ def rasterize_bwd(means2d, conics, colors, opacities, betas, backgrounds, masks,
     v_colors = torch.zeros_like(colors)
     v_opacities = torch.zeros_like(opacities)
     v_betas = torch.zeros_like(betas)
-    check(lib.ubs_rasterize_bwd(C, N, ptr(n_isects_dev), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
+    check(lib.ubs_rasterize_bwd(C, N, ptr(n_isects_dev), flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
                                 ptr(betas), ptr(backgrounds), ptr(masks), ch, int(width), int(height), int(tile_size),
                                 ptr(isect_offsets), ptr(flatten_ids), ptr(render_alphas), ptr(last_ids),
                                 ptr(_req(v_render_colors, "v_render_colors")),
