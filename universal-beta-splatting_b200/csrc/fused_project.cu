@@ -194,6 +194,208 @@ fused_project_fwd_kernel(int C, int64_t N, const float *__restrict__ records, co
     }
 }
 
+
+__device__ __forceinline__ void tma_bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// Backward of fused_project_fwd_kernel: one thread per primitive, looping over cameras, so the per-primitive sums
+// need no atomics.  Recomputes the cheap forward intermediates from the record instead of storing them.
+template <int D>
+__global__ void __launch_bounds__(kFusedThreads)
+fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records, const float *__restrict__ viewmats,
+                         const float *__restrict__ Ks, const float *__restrict__ cam_pos,
+                         const float *__restrict__ timestamps, uint32_t width, uint32_t height, float eps2d,
+                         int calc_comp, const int32_t *__restrict__ radii, const float *__restrict__ conics,
+                         const float *__restrict__ v_means2d, const float *__restrict__ v_depths,
+                         const float *__restrict__ v_conics, const float *__restrict__ v_opacities,
+                         const float *__restrict__ v_betas, const float *__restrict__ v_colors,
+                         float *__restrict__ v_records) {
+    constexpr int Cd = D - 3, M = NdDims<D>::M;
+    constexpr int STRIDE = UBS_RECORD_STRIDE(D);
+    __shared__ __align__(128) float s_rec[kFusedThreads * STRIDE];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int64_t base = (int64_t)blockIdx.x * kFusedThreads;
+    const int n_here = (int)min((int64_t)kFusedThreads, N - base);
+    const uint32_t bytes = (uint32_t)n_here * STRIDE * sizeof(float);
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar, bytes);
+        tma_bulk_g2s(s_rec, records + base * STRIDE, bytes, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+
+    const int64_t gid = base + threadIdx.x;
+    const bool active = threadIdx.x < n_here;
+    float grad[STRIDE];
+#pragma unroll
+    for (int k = 0; k < STRIDE; ++k) grad[k] = 0.f;
+
+    if (active) {
+        float rec[STRIDE];
+        const float4 *src = reinterpret_cast<const float4 *>(s_rec + threadIdx.x * STRIDE);
+#pragma unroll
+        for (int k = 0; k < STRIDE / 4; ++k) {
+            const float4 v = src[k];
+            rec[4 * k + 0] = v.x, rec[4 * k + 1] = v.y, rec[4 * k + 2] = v.z, rec[4 * k + 3] = v.w;
+        }
+        // ---- recompute the camera-independent forward state ------------------------------------------------
+        float xyz[3], mu2[Cd], beta_c[Cd], s[D], lt[M];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) xyz[k] = rec[k];
+#pragma unroll
+        for (int k = 0; k < Cd; ++k) mu2[k] = rec[3 + k];
+        const float o_in = sigmoid_f(rec[D + 3]);
+        const float beta0 = beta_act_f(rec[D + 4]);
+#pragma unroll
+        for (int k = 0; k < Cd; ++k) beta_c[k] = beta_act_f(rec[D + 5 + k]);
+#pragma unroll
+        for (int k = 0; k < D; ++k) s[k] = softplus_f(rec[2 * D + 2 + k]);
+#pragma unroll
+        for (int k = 0; k < M; ++k) lt[k] = rec[3 * D + 2 + k];
+        const float R[9] = {1.f, lt[0], lt[1], -lt[0], 1.f, lt[2], -lt[1], -lt[2], 1.f};
+        float L[D * D], S[D * D];
+        build_L<D>(R, s, lt, L);
+        covar_from_L<D>(L, s, S, D);
+        float V11[9], V12[3 * Cd], V21[Cd * 3], V22[Cd * Cd];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) V11[r * 3 + c] = S[r * D + c];
+#pragma unroll
+            for (int c = 0; c < Cd; ++c) {
+                V12[r * Cd + c] = S[r * D + 3 + c];
+                V21[c * 3 + r] = S[(3 + c) * D + r];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < Cd; ++r)
+#pragma unroll
+            for (int c = 0; c < Cd; ++c) V22[r * Cd + c] = S[(3 + r) * D + 3 + c];
+        CondPrep<Cd> prep;
+        cond_prepare<Cd>(V11, V12, V21, V22, beta_c, prep);
+        const float s6[6] = {prep.cov[0], prep.cov[1], prep.cov[2], prep.cov[4], prep.cov[5], prep.cov[8]};
+
+        // ---- accumulate over cameras ------------------------------------------------------------------------
+        float G[D * D];  // gradient w.r.t. the full D x D covariance
+#pragma unroll
+        for (int k = 0; k < D * D; ++k) G[k] = 0.f;
+        float g_mu[D], g_o = 0.f, g_beta0 = 0.f, g_beta_c[Cd], g_rgb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < D; ++k) g_mu[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < Cd; ++k) g_beta_c[k] = 0.f;
+
+        for (int cid = 0; cid < C; ++cid) {
+            const int64_t idx = (int64_t)cid * N + gid;
+            if (radii[idx] <= 0) continue;
+            const Cam cam = load_cam(viewmats + cid * 16, Ks + cid * 9);
+            float x[Cd];
+            {
+                const float dx = xyz[0] - cam_pos[cid * 3 + 0], dy = xyz[1] - cam_pos[cid * 3 + 1],
+                            dz = xyz[2] - cam_pos[cid * 3 + 2];
+                const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+                x[0] = __fdiv_rn(dx, nrm) - mu2[0];
+                x[1] = __fdiv_rn(dy, nrm) - mu2[1];
+                x[2] = __fdiv_rn(dz, nrm) - mu2[2];
+                if constexpr (Cd > 3) {
+                    x[3] = timestamps[cid] - mu2[3];
+#pragma unroll
+                    for (int k = 4; k < Cd; ++k) x[k] = -mu2[k];
+                }
+            }
+            float mean[3], o_cond;
+            cond_apply<Cd>(prep, xyz, x, o_in, beta_c, mean, o_cond);
+
+            const float conic[3] = {conics[idx * 3], conics[idx * 3 + 1], conics[idx * 3 + 2]};
+            const float vm[2] = {v_means2d[idx * 2], v_means2d[idx * 2 + 1]};
+            const float vc[3] = {v_conics[idx * 3], v_conics[idx * 3 + 1], v_conics[idx * 3 + 2]};
+            float v_o = v_opacities[idx];
+            float comp = 0.f, v_comp = 0.f;
+            if (calc_comp) {
+                const Splat2D f = project_splat(cam, mean, s6, width, height, eps2d, -3.0e38f, 3.0e38f, -1.f);
+                comp = f.compensation;
+                v_comp = v_o * o_cond;
+                v_o = v_o * comp;
+            }
+            float v_mean[3] = {0.f, 0.f, 0.f}, v_s6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            project_splat_vjp(cam, mean, s6, width, height, eps2d, conic, calc_comp ? &comp : nullptr, vm,
+                              v_depths != nullptr ? v_depths[idx] : 0.f, vc, calc_comp ? &v_comp : nullptr, v_mean,
+                              v_s6, nullptr, nullptr);
+            // index-backward of the 3x3 -> 6 gather: only the upper triangle receives gradient (rendering.py:55-56)
+            const float gV[9] = {v_s6[0], v_s6[1], v_s6[2], 0.f, v_s6[3], v_s6[4], 0.f, 0.f, v_s6[5]};
+            float g_mu1[3], g_mu2[Cd], g11[9], g12[3 * Cd], g21[Cd * 3], g22[Cd * Cd], go, gb[Cd];
+            cond_backward<Cd>(x, V12, V21, V22, o_in, beta_c, v_mean, gV, v_o, g_mu1, g_mu2, g11, g12, g21, g22, go, gb);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) g_mu[k] += g_mu1[k];
+#pragma unroll
+            for (int k = 0; k < Cd; ++k) {
+                g_mu[3 + k] += g_mu2[k];
+                g_beta_c[k] += gb[k];
+            }
+            g_o += go;
+            g_beta0 += v_betas[idx];
+            if (v_colors != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g_rgb[k] += v_colors[idx * 3 + k];
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) G[r * D + c] += g11[r * 3 + c];
+#pragma unroll
+                for (int c = 0; c < Cd; ++c) {
+                    G[r * D + 3 + c] += g12[r * Cd + c];
+                    G[(3 + c) * D + r] += g21[c * 3 + r];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < Cd; ++r)
+#pragma unroll
+                for (int c = 0; c < Cd; ++c) G[(3 + r) * D + 3 + c] += g22[r * Cd + c];
+        }
+
+        // ---- covariance build, K1 and activation backward ---------------------------------------------------
+        float vR[9], vs[D], vlt[M];
+        covar_vjp<D>(R, s, L, G, D, vR, vs, vlt);
+        vlt[0] += vR[1] - vR[3];
+        vlt[1] += vR[2] - vR[6];
+        vlt[2] += vR[5] - vR[7];
+#pragma unroll
+        for (int k = 0; k < D; ++k) grad[k] = g_mu[k];  // xyz | mean (no gradient through the view direction)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) grad[D + k] = g_rgb[k];
+        grad[D + 3] = g_o * o_in * (1.f - o_in);  // sigmoid'
+        grad[D + 4] = g_beta0 * beta0;             // d(4 e^x)/dx = 4 e^x
+#pragma unroll
+        for (int k = 0; k < Cd; ++k) grad[D + 5 + k] = g_beta_c[k] * beta_c[k];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float raw = rec[2 * D + 2 + k];
+            grad[2 * D + 2 + k] = vs[k] * (raw > 20.f ? 1.f : sigmoid_f(raw));  // softplus'
+        }
+#pragma unroll
+        for (int k = 0; k < M; ++k) grad[3 * D + 2 + k] = vlt[k];
+    }
+
+    // ---- stage the gradient records in shared memory and write them with one TMA bulk store --------------------
+    __syncthreads();  // all record reads done; reuse s_rec
+    if (active) {
+        float4 *dst = reinterpret_cast<float4 *>(s_rec + threadIdx.x * STRIDE);
+#pragma unroll
+        for (int k = 0; k < STRIDE / 4; ++k) dst[k] = make_float4(grad[4 * k], grad[4 * k + 1], grad[4 * k + 2], grad[4 * k + 3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) tma_bulk_s2g(v_records + base * STRIDE, s_rec, bytes);
+}
+
 }  // namespace
 }  // namespace ubs
 
@@ -243,4 +445,34 @@ extern "C" int ubs_fused_project_fwd(int C, int64_t N, int D, const float *recor
 #undef UBS_FUSED_LAUNCH
     UBS_LAUNCH_CHECK("fused_project_fwd_kernel");
     return isect_blocksums_from_counts(CN, tiles_per_gauss, workspace, n_isects, s);
+}
+
+extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const float *viewmats,
+                                     const float *Ks, const float *cam_pos, const float *timestamps, int width,
+                                     int height, float eps2d, int calc_compensations, const int32_t *radii,
+                                     const float *conics, const float *v_means2d, const float *v_depths,
+                                     const float *v_conics, const float *v_opacities, const float *v_betas,
+                                     const float *v_colors, float *v_records, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "fused_project_bwd: bad sizes");
+    UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd: D must be 6 or 7 (got %d)", D);
+    if (N == 0) return UBS_OK;
+    UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && conics && v_means2d && v_conics && v_opacities &&
+                      v_betas && v_records,
+                  "fused_project_bwd: null pointer");
+    UBS_CHECK_ARG(D != 7 || timestamps != nullptr, "fused_project_bwd: D=7 needs timestamps");
+    UBS_CHECK_ARG((((uintptr_t)records | (uintptr_t)v_records) & 15) == 0,
+                  "fused_project_bwd: records / v_records must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
+    if (D == 6)
+        fused_project_bwd_kernel<6><<<gx, kFusedThreads, 0, s>>>(
+            C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
+            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records);
+    else
+        fused_project_bwd_kernel<7><<<gx, kFusedThreads, 0, s>>>(
+            C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
+            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records);
+    UBS_LAUNCH_CHECK("fused_project_bwd_kernel");
+    return UBS_OK;
 }

@@ -1,0 +1,299 @@
+// K11: backward of the per-tile compositing.  Drop-in for rasterize_to_pixels_bwd (rasterize_to_pixels_bwd.cu:16-276):
+// re-walks each tile back to front from T_final / last_ids and produces gradients of means2d, conics, colours,
+// opacities and betas (accumulated into caller-zeroed arrays).
+//
+// Reduction strategy (the reference does 50 SHFL + up to 8x10 global atomics per (tile, pair)):
+//   1. each warp owns an 8x4 pixel sub-tile and first compacts the batch to the pairs whose sigma < 1 support can
+//      touch it (same cull as the forward pass), so most (warp, pair) combinations cost nothing;
+//   2. for 3 channels, three pairs x 10 gradient components are reduced together with one 31-shuffle transposing
+//      butterfly, after which lane l holds the warp total of component l;
+//   3. 30 lanes add those totals into a shared-memory accumulator [pair][component] in one instruction;
+//   4. after the batch, each thread flushes one pair with at most 10 global atomics -- one set per (tile, pair).
+#include "common.cuh"
+#include "raster_common.cuh"
+
+namespace ubs {
+namespace {
+
+constexpr int kGrad3 = 10;  // rgb(3) conic(3) xy(2) opacity beta
+
+template <int CH>
+__global__ void __launch_bounds__(kTilePixels)
+rasterize_bwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev, int64_t isect_capacity,
+                     const float2 *__restrict__ means2d, const float *__restrict__ conics,
+                     const float *__restrict__ colors, const float *__restrict__ opacities,
+                     const float *__restrict__ betas, const float *__restrict__ backgrounds,
+                     const uint8_t *__restrict__ masks, uint32_t width, uint32_t height, uint32_t tile_width,
+                     uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
+                     const int32_t *__restrict__ flatten_ids, const float *__restrict__ render_alphas,
+                     const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
+                     const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
+                     float *__restrict__ v_conics, float *__restrict__ v_colors, float *__restrict__ v_opacities,
+                     float *__restrict__ v_betas) {
+    constexpr int NG = 7 + CH;           // gradient components per pair
+    constexpr bool kSmemAcc = CH <= 4;   // wide colour vectors go straight to global atomics (shared memory budget)
+    const uint32_t cam = blockIdx.z;
+    const uint32_t tile_id = blockIdx.y * tile_width + blockIdx.x;
+    const uint32_t tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
+    const SubTile st = sub_tile_of(tr);
+    const uint32_t i = blockIdx.y * kTile + st.py;
+    const uint32_t j = blockIdx.x * kTile + st.px;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const bool inside = (i < height && j < width);
+
+    tile_offsets += (size_t)cam * tile_height * tile_width;
+    if (backgrounds != nullptr) backgrounds += cam * CH;
+    if (masks != nullptr && !masks[(size_t)cam * tile_height * tile_width + tile_id]) return;
+
+    const int64_t n_isects = min(*n_isects_dev, isect_capacity);
+    const int32_t range_start = tile_offsets[tile_id];
+    const int32_t range_end = (cam == (uint32_t)C - 1 && tile_id == tile_width * tile_height - 1)
+                                  ? (int32_t)n_isects
+                                  : tile_offsets[tile_id + 1];
+    const int32_t num_batches = (range_end - range_start + kTilePixels - 1) / kTilePixels;
+    if (num_batches <= 0) return;
+
+    __shared__ int32_t s_id[kTilePixels];
+    __shared__ float4 s_xyob[kTilePixels];
+    __shared__ float4 s_conic[kTilePixels];
+    __shared__ float4 s_bbox[kTilePixels];
+    __shared__ float s_color[kTilePixels * CH];
+    __shared__ float s_acc[kSmemAcc ? kTilePixels * NG : 1];
+    __shared__ uint8_t s_list[kTilePixels / 32][kTilePixels];
+
+    const float wx0 = (float)(blockIdx.x * kTile + st.bx * kSubW) + 0.5f, wx1 = wx0 + (float)(kSubW - 1);
+    const float wy0 = (float)(blockIdx.y * kTile + st.by * kSubH) + 0.5f, wy1 = wy0 + (float)(kSubH - 1);
+
+    // per-pixel state
+    const size_t pix = inside ? ((size_t)cam * height + i) * width + j : 0;
+    const float T_final = inside ? 1.f - render_alphas[pix] : 1.f;
+    float T = T_final;
+    float buffer[CH], v_rc[CH];
+    float bg_dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        buffer[k] = 0.f;
+        v_rc[k] = inside ? v_render_colors[pix * CH + k] : 0.f;
+        if (backgrounds != nullptr) bg_dot += backgrounds[k] * v_rc[k];
+    }
+    const float v_ra = inside ? v_render_alphas[pix] : 0.f;
+    const int32_t bin_final = inside ? last_ids[pix] : 0;
+    int32_t warp_bin_final = bin_final;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, off));
+
+    if constexpr (kSmemAcc)
+        for (int k = tr; k < kTilePixels * NG; k += kTilePixels) s_acc[k] = 0.f;
+
+    // gradient of one (pixel, pair); writes NG values (zeros when the pair does not contribute to the pixel)
+    auto pair_grad = [&](uint32_t p, int32_t batch_end, float *g) {
+#pragma unroll
+        for (int k = 0; k < NG; ++k) g[k] = 0.f;
+        if (!inside || batch_end - (int32_t)p > bin_final) return false;
+        const float4 conic = s_conic[p];
+        const float4 xyob = s_xyob[p];
+        const float opac = xyob.z, beta = xyob.w;
+        const float dx = xyob.x - px, dy = xyob.y - py;
+        const float sigma = (conic.x * dx * dx + conic.z * dy * dy) + 2.f * conic.y * dx * dy;
+        if (sigma < 0.f || sigma >= 1.f) return false;
+        const float vis = __powf(1.f - sigma, beta);
+        const float alpha = fminf(0.999f, opac * vis);
+        const float ra = 1.f / (1.f - alpha);
+        T *= ra;
+        const float fac = alpha * T;
+        float v_alpha = 0.f;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const float c = s_color[p * CH + k];
+            g[k] = fac * v_rc[k];
+            v_alpha += (c * T - buffer[k] * ra) * v_rc[k];
+            buffer[k] += c * fac;
+        }
+        v_alpha += T_final * ra * v_ra;
+        if (backgrounds != nullptr) v_alpha += -T_final * ra * bg_dot;
+        if (opac * vis <= 0.999f) {
+            const float v_sigma = -v_alpha * opac * beta * __powf(1.f - sigma, beta - 1.f);
+            g[CH + 0] = dx * dx * v_sigma;
+            g[CH + 1] = 2.f * dx * dy * v_sigma;
+            g[CH + 2] = dy * dy * v_sigma;
+            g[CH + 3] = 2.f * v_sigma * (conic.x * dx + conic.y * dy);
+            g[CH + 4] = 2.f * v_sigma * (conic.y * dx + conic.z * dy);
+            g[CH + 5] = vis * v_alpha;
+            g[CH + 6] = v_alpha * opac * vis * __logf(1.f - sigma);
+        }
+        return true;
+    };
+
+    for (int32_t b = 0; b < num_batches; ++b) {
+        __syncthreads();  // previous batch fully consumed and flushed
+        const int32_t batch_end = range_end - 1 - kTilePixels * b;  // pair index held by slot 0 (furthest back)
+        const int32_t batch_size = min((int32_t)kTilePixels, batch_end + 1 - range_start);
+        const int32_t idx = batch_end - (int32_t)tr;
+        if (idx >= range_start) {
+            const int32_t g = flatten_ids[idx];
+            s_id[tr] = g;
+            const float2 xy = means2d[g];
+            const float4 cn = make_float4(conics[(size_t)g * 3], conics[(size_t)g * 3 + 1], conics[(size_t)g * 3 + 2], 0.f);
+            s_xyob[tr] = make_float4(xy.x, xy.y, opacities[g], betas[g]);
+            s_conic[tr] = cn;
+            s_bbox[tr] = support_bbox(xy.x, xy.y, cn.x, cn.y, cn.z);
+#pragma unroll
+            for (int k = 0; k < CH; ++k) s_color[tr * CH + k] = colors[(size_t)g * CH + k];
+        }
+        __syncthreads();
+
+        // pairs behind every pixel's last contributor are skipped outright (rasterize_to_pixels_bwd.cu:157)
+        const int32_t t_begin = max(0, batch_end - warp_bin_final);
+        uint32_t cnt = 0;
+        for (int32_t p0 = t_begin & ~31; p0 < batch_size; p0 += 32) {
+            const int32_t p = p0 + (int32_t)lane;
+            bool hit = false;
+            if (p >= t_begin && p < batch_size) {
+                const float4 bb = s_bbox[p];
+                hit = (bb.x <= wx1) && (bb.y >= wx0) && (bb.z <= wy1) && (bb.w >= wy0);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (hit) s_list[warp][cnt + __popc(m & ((1u << lane) - 1u))] = (uint8_t)p;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+
+        if constexpr (CH == 3) {
+            for (uint32_t t = 0; t < cnt; t += 3) {
+                float v[32];
+                v[30] = 0.f, v[31] = 0.f;
+                bool any_valid = false;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (t + q < cnt) {
+                        any_valid |= pair_grad(s_list[warp][t + q], batch_end, v + q * kGrad3);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kGrad3; ++k) v[q * kGrad3 + k] = 0.f;
+                    }
+                }
+                if (!__any_sync(0xffffffffu, any_valid)) continue;
+                // transposing butterfly: afterwards v[0] of lane l is the warp-wide sum of component l
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool upper = (lane & off) != 0;
+#pragma unroll
+                    for (int k = 0; k < off; ++k) {
+                        const float send = upper ? v[k] : v[k + off];
+                        const float keep = upper ? v[k + off] : v[k];
+                        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                const uint32_t q = lane / kGrad3, comp = lane - q * kGrad3;
+                if (lane < 3 * kGrad3 && t + q < cnt && v[0] != 0.f)
+                    atomicAdd(&s_acc[(uint32_t)s_list[warp][t + q] * NG + comp], v[0]);
+            }
+        } else {
+            for (uint32_t t = 0; t < cnt; ++t) {
+                float g[NG];
+                const uint32_t p = s_list[warp][t];
+                const bool valid = pair_grad(p, batch_end, g);
+                if (!__any_sync(0xffffffffu, valid)) continue;
+#pragma unroll
+                for (int k = 0; k < NG; ++k) {
+                    float x = g[k];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+                    if (lane == 0 && x != 0.f) {
+                        if constexpr (kSmemAcc) {
+                            atomicAdd(&s_acc[p * NG + k], x);
+                        } else {
+                            const size_t g_id = (size_t)s_id[p];
+                            float *dst = k < CH       ? v_colors + g_id * CH + k
+                                         : k < CH + 3 ? v_conics + g_id * 3 + (k - CH)
+                                         : k < CH + 5 ? v_means2d + g_id * 2 + (k - CH - 3)
+                                         : k == CH + 5 ? v_opacities + g_id
+                                                       : v_betas + g_id;
+                            atomicAdd(dst, x);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // flush: one set of global atomics per (tile, pair)
+        if (kSmemAcc && (int32_t)tr < batch_size) {
+            const int32_t g = s_id[tr];
+            float *acc = s_acc + tr * NG;
+            bool nz = false;
+#pragma unroll
+            for (int k = 0; k < NG; ++k) nz |= (acc[k] != 0.f);
+            if (nz) {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) atomicAdd(v_colors + (size_t)g * CH + k, acc[k]);
+                atomicAdd(v_conics + (size_t)g * 3 + 0, acc[CH + 0]);
+                atomicAdd(v_conics + (size_t)g * 3 + 1, acc[CH + 1]);
+                atomicAdd(v_conics + (size_t)g * 3 + 2, acc[CH + 2]);
+                atomicAdd(v_means2d + (size_t)g * 2 + 0, acc[CH + 3]);
+                atomicAdd(v_means2d + (size_t)g * 2 + 1, acc[CH + 4]);
+                atomicAdd(v_opacities + g, acc[CH + 5]);
+                atomicAdd(v_betas + g, acc[CH + 6]);
+#pragma unroll
+                for (int k = 0; k < NG; ++k) acc[k] = 0.f;
+            }
+        }
+    }
+}
+
+template <int CH>
+int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const float *means2d, const float *conics,
+               const float *colors, const float *opacities, const float *betas, const float *backgrounds,
+               const uint8_t *masks, int width, int height, const int32_t *offsets, const int32_t *flatten_ids,
+               const float *render_alphas, const int32_t *last_ids, const float *v_render_colors,
+               const float *v_render_alphas, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+               float *v_betas, cudaStream_t s) {
+    const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
+    dim3 grid(tw, th, (unsigned)C), block(kTilePixels, 1, 1);
+    rasterize_bwd_kernel<CH><<<grid, block, 0, s>>>(
+        C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities, betas, backgrounds, masks,
+        (uint32_t)width, (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids, v_render_colors,
+        v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas);
+    UBS_LAUNCH_CHECK("rasterize_bwd_kernel");
+    return UBS_OK;
+}
+
+}  // namespace
+}  // namespace ubs
+
+extern "C" int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
+                                 const float *means2d, const float *conics, const float *colors,
+                                 const float *opacities, const float *betas, const float *backgrounds,
+                                 const uint8_t *masks, int channels, int width, int height, int tile_size,
+                                 const int32_t *offsets, const int32_t *flatten_ids, const float *render_alphas,
+                                 const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
+                                 float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+                                 float *v_betas, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "rasterize_bwd: bad sizes");
+    UBS_CHECK_ARG(tile_size == kTile, "rasterize_bwd: tile_size must be %d (got %d)", kTile, tile_size);
+    if (C == 0 || N == 0) return UBS_OK;
+    UBS_CHECK_ARG(n_isects && offsets && means2d && conics && colors && opacities && betas && flatten_ids &&
+                      render_alphas && last_ids && v_render_colors && v_render_alphas && v_means2d && v_conics &&
+                      v_colors && v_opacities && v_betas,
+                  "rasterize_bwd: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+#define UBS_BWD_CASE(CH)                                                                                               \
+    case CH:                                                                                                           \
+        return launch_bwd<CH>(C, N, n_isects, isect_capacity, means2d, conics, colors, opacities, betas, backgrounds,  \
+                              masks, width, height, offsets, flatten_ids, render_alphas, last_ids, v_render_colors,    \
+                              v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas, s);
+    switch (channels) {
+        UBS_BWD_CASE(1)
+        UBS_BWD_CASE(2)
+        UBS_BWD_CASE(3)
+        UBS_BWD_CASE(4)
+        UBS_BWD_CASE(8)
+        UBS_BWD_CASE(16)
+        UBS_BWD_CASE(32)
+        default:
+            set_error("rasterize_bwd: unsupported channel count %d (supported: 1,2,3,4,8,16,32)", channels);
+            return UBS_EUNSUPPORTED;
+    }
+#undef UBS_BWD_CASE
+}

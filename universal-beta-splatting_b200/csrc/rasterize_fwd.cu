@@ -2,8 +2,9 @@
 // Drop-in for rasterize_to_pixels_fwd (rasterize_to_pixels_fwd.cu:16-191): same sigma, alpha, early-termination
 // and last_ids semantics.  Differences in *how*: colours are staged through shared memory with the rest of the
 // 2-D record (the reference re-reads them from global memory per accepted pair), the gather of batch b+1 is
-// issued before batch b is composited (register double-buffering), and a warp whose 32 pixels are all done skips
-// the batch instead of spinning through it.
+// issued before batch b is composited (register double-buffering), each warp owns an 8x4 pixel sub-tile and first
+// compacts the batch to the pairs whose sigma < 1 ellipse can touch those 32 pixels (the tile lists themselves stay
+// bit-identical to the reference's -- the cull is internal), and a warp whose pixels are all done skips the batch.
 #include "common.cuh"
 #include "raster_common.cuh"
 
@@ -14,19 +15,19 @@ namespace {
 template <int CH>
 __global__ void __launch_bounds__(kTilePixels)
 rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev, int64_t isect_capacity,
-                     const float2 *__restrict__ means2d,
-                     const float *__restrict__ conics, const float *__restrict__ colors,
-                     const float *__restrict__ opacities, const float *__restrict__ betas,
-                     const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, uint32_t width,
-                     uint32_t height, uint32_t tile_width, uint32_t tile_height,
-                     const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
-                     float *__restrict__ render_colors, float *__restrict__ render_alphas,
-                     int32_t *__restrict__ last_ids) {
+                     const float2 *__restrict__ means2d, const float *__restrict__ conics,
+                     const float *__restrict__ colors, const float *__restrict__ opacities,
+                     const float *__restrict__ betas, const float *__restrict__ backgrounds,
+                     const uint8_t *__restrict__ masks, uint32_t width, uint32_t height, uint32_t tile_width,
+                     uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
+                     const int32_t *__restrict__ flatten_ids, float *__restrict__ render_colors,
+                     float *__restrict__ render_alphas, int32_t *__restrict__ last_ids) {
     const uint32_t cam = blockIdx.z;
     const uint32_t tile_id = blockIdx.y * tile_width + blockIdx.x;
-    const uint32_t tr = threadIdx.y * kTile + threadIdx.x;
-    const uint32_t i = blockIdx.y * kTile + threadIdx.y;
-    const uint32_t j = blockIdx.x * kTile + threadIdx.x;
+    const uint32_t tr = threadIdx.x;
+    const SubTile st = sub_tile_of(tr);
+    const uint32_t i = blockIdx.y * kTile + st.py;
+    const uint32_t j = blockIdx.x * kTile + st.px;
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
     const bool inside = (i < height && j < width);
     const size_t pix = ((size_t)cam * height + i) * width + j;
@@ -51,9 +52,16 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
     const int32_t n_pairs = range_end - range_start;
     const int32_t num_batches = (n_pairs + kTilePixels - 1) / kTilePixels;
 
-    __shared__ float4 s_xyob[kTilePixels];      // mean2d.x, mean2d.y, opacity, beta
-    __shared__ float4 s_conic[kTilePixels];     // conic a, b, c, (unused)
+    __shared__ float4 s_xyob[kTilePixels];   // mean2d.x, mean2d.y, opacity, beta
+    __shared__ float4 s_conic[kTilePixels];  // conic a, b, c, (unused)
+    __shared__ float4 s_bbox[kTilePixels];   // xmin, xmax, ymin, ymax of the sigma < 1 ellipse (inflated)
     __shared__ float s_color[kTilePixels * CH];
+    __shared__ uint8_t s_list[kTilePixels / 32][kTilePixels];  // per-warp compacted pair indices
+
+    // pixel-centre rectangle of this warp's 8x4 sub-tile
+    const float wx0 = (float)(blockIdx.x * kTile + st.bx * kSubW) + 0.5f, wx1 = wx0 + (float)(kSubW - 1);
+    const float wy0 = (float)(blockIdx.y * kTile + st.by * kSubH) + 0.5f, wy1 = wy0 + (float)(kSubH - 1);
+    const uint32_t lane = tr & 31, warp = tr >> 5;
 
     float T = 1.f;
     int32_t cur_idx = 0;
@@ -85,6 +93,7 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         if (__syncthreads_count(done) >= kTilePixels) break;
         s_xyob[tr] = r_xyob;
         s_conic[tr] = r_conic;
+        s_bbox[tr] = support_bbox(r_xyob.x, r_xyob.y, r_conic.x, r_conic.y, r_conic.z);
 #pragma unroll
         for (int k = 0; k < CH; ++k) s_color[tr * CH + k] = r_color[k];
         __syncthreads();
@@ -93,9 +102,26 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         const int32_t batch_start = range_start + b * kTilePixels;
         const int32_t batch_size = min((int32_t)kTilePixels, range_end - batch_start);
         if (__all_sync(0xffffffffu, done)) continue;  // whole warp finished: nothing to composite
-        for (int32_t t = 0; t < batch_size && !done; ++t) {
-            const float4 conic = s_conic[t];
-            const float4 xyob = s_xyob[t];
+
+        // warp-level cull: keep (in order) only the pairs whose support touches this warp's 8x4 pixels
+        uint32_t cnt = 0;
+        for (int32_t p0 = 0; p0 < batch_size; p0 += 32) {
+            const int32_t p = p0 + (int32_t)lane;
+            bool hit = false;
+            if (p < batch_size) {
+                const float4 bb = s_bbox[p];
+                hit = (bb.x <= wx1) && (bb.y >= wx0) && (bb.z <= wy1) && (bb.w >= wy0);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (hit) s_list[warp][cnt + __popc(m & ((1u << lane) - 1u))] = (uint8_t)p;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+
+        for (uint32_t t = 0; t < cnt && !done; ++t) {
+            const uint32_t p = s_list[warp][t];
+            const float4 conic = s_conic[p];
+            const float4 xyob = s_xyob[p];
             const float dx = xyob.x - px, dy = xyob.y - py;
             const float sigma = (conic.x * dx * dx + conic.z * dy * dy) + 2.f * conic.y * dx * dy;
             if (sigma < 0.f || sigma >= 1.f) continue;
@@ -107,8 +133,8 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
             }
             const float vis = alpha * T;
 #pragma unroll
-            for (int k = 0; k < CH; ++k) pix_out[k] += s_color[t * CH + k] * vis;
-            cur_idx = batch_start + t;
+            for (int k = 0; k < CH; ++k) pix_out[k] += s_color[p * CH + k] * vis;
+            cur_idx = batch_start + (int32_t)p;
             T = next_T;
         }
     }
@@ -128,7 +154,7 @@ int launch_fwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
                const uint8_t *masks, int width, int height, const int32_t *offsets, const int32_t *flatten_ids,
                float *render_colors, float *render_alphas, int32_t *last_ids, cudaStream_t s) {
     const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
-    dim3 grid(tw, th, (unsigned)C), block(kTile, kTile, 1);
+    dim3 grid(tw, th, (unsigned)C), block(kTilePixels, 1, 1);
     rasterize_fwd_kernel<CH><<<grid, block, 0, s>>>(C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities,
                                                     betas, backgrounds, masks, (uint32_t)width, (uint32_t)height, tw,
                                                     th, offsets, flatten_ids, render_colors, render_alphas, last_ids);

@@ -144,3 +144,70 @@ class FusedRasterizer:
             self._count_event = torch.cuda.Event()
             self._count_event.record()
         return self.render_colors, self.render_alphas
+
+    def _grad_buffers(self):
+        if getattr(self, "_gflat", None) is None:
+            C, N = self.C, self.N
+            self._gflat = torch.empty((C * N * 10,), dtype=torch.float32, device=self.device)
+            o = 0
+            views = []
+            for w, shape in ((2, (C, N, 2)), (3, (C, N, 3)), (3, (C, N, 3)), (1, (C, N)), (1, (C, N))):
+                views.append(self._gflat[o:o + C * N * w].view(shape))
+                o += C * N * w
+            self.v_means2d, self.v_conics, self.v_colors, self.v_opacities, self.v_betas = views
+        return self._gflat
+
+    @torch.no_grad()
+    def backward(self, records: Tensor, viewmats: Tensor, Ks: Tensor, cam_pos: Tensor, timestamps: Optional[Tensor],
+                 backgrounds: Optional[Tensor], v_render_colors: Tensor, v_render_alphas: Tensor,
+                 v_records: Optional[Tensor] = None) -> Tensor:
+        """Gradient of the most recent forward() w.r.t. the packed records ([N, stride], same layout).
+        Must be called before the next forward(): it reuses that frame's tile lists and screen-space records."""
+        lib, s = self.lib, torch.cuda.current_stream().cuda_stream
+        C, N, D = self.C, self.N, self.D
+        self._grad_buffers().zero_()  # one memset for all five screen-space gradient arrays
+        v_rc = v_render_colors.contiguous()
+        v_ra = v_render_alphas.contiguous()
+        assert v_rc.shape == (C, self.H, self.W, 3) and v_ra.shape == (C, self.H, self.W, 1)
+        check(lib.ubs_rasterize_bwd(
+            C, N, ptr(self.n_isects), self.capacity, ptr(self.means2d), ptr(self.conics), ptr(self.colors),
+            ptr(self.opacities), ptr(self.betas), ptr(backgrounds), None, 3, self.W, self.H, self.tile_size,
+            ptr(self.offsets), ptr(self.flatten_ids), ptr(self.render_alphas), ptr(self.last_ids), ptr(v_rc),
+            ptr(v_ra), ptr(self.v_means2d), ptr(self.v_conics), ptr(self.v_colors), ptr(self.v_opacities),
+            ptr(self.v_betas), s), "ubs_rasterize_bwd")
+        if v_records is None:
+            v_records = torch.empty_like(records)
+        check(lib.ubs_fused_project_bwd(
+            C, N, D, ptr(records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), self.W, self.H, self.eps2d,
+            1 if self.aa else 0, ptr(self.radii), ptr(self.conics), ptr(self.v_means2d), None, ptr(self.v_conics),
+            ptr(self.v_opacities), ptr(self.v_betas), ptr(self.v_colors), ptr(v_records), s), "ubs_fused_project_bwd")
+        return v_records
+
+
+class _FusedRender(torch.autograd.Function):
+    """records -> (render_colors, render_alphas) with gradients to the packed records and the backgrounds."""
+
+    @staticmethod
+    def forward(ctx, records, rz, viewmats, Ks, cam_pos, timestamps, backgrounds):
+        rc, ra = rz.forward(records, viewmats, Ks, cam_pos, timestamps, backgrounds)
+        ctx.rz = rz
+        ctx.save_for_backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds)
+        return rc, ra
+
+    @staticmethod
+    def backward(ctx, v_rc, v_ra):
+        records, viewmats, Ks, cam_pos, timestamps, backgrounds = ctx.saved_tensors
+        rz = ctx.rz
+        v_records = rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, v_rc, v_ra)
+        v_bg = None
+        if backgrounds is not None and ctx.needs_input_grad[6]:
+            v_bg = (v_rc * (1.0 - rz.render_alphas)).sum(dim=(1, 2))
+        return v_records, None, None, None, None, None, v_bg
+
+
+def render(records: Tensor, rz: FusedRasterizer, viewmats: Tensor, Ks: Tensor, cam_pos: Tensor,
+           timestamps: Optional[Tensor] = None, backgrounds: Optional[Tensor] = None):
+    """Differentiable fused render: the equivalent of BetaModel.render (scene/beta_model.py:660-722) for C cameras
+    at once.  Returns (render_colors [C,H,W,3], render_alphas [C,H,W,1]); the buffers belong to `rz` and are
+    overwritten by its next forward()."""
+    return _FusedRender.apply(records, rz, viewmats, Ks, cam_pos, timestamps, backgrounds)
