@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: rendered frames/s (and forward+backward it/s) at 3M 6-D Beta primitives, 1920x1080.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this library (CUDA, sm_100a)
+    python bench.py --impl reference ...                                # the CPU oracle port on the host cores
+    python bench.py --impl reference_cuda ...                           # the reference's own CUDA kernels (if built)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...    # one rank per GPU (camera-parallel)
+
+One "step" = one camera rendered per GPU (a different camera of a 64-camera ring every step and rank); the scene
+(parameter records, 432 MB) is resident in HBM and is larger than L2, so no L2 flush is needed between steps.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "universal-beta-splatting_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name -> (synth config, description)
+    "cfg3": ("cfg3", "BASELINE configs[2]/[4]: 3M 6-D Beta primitives (unbounded), 1920x1080, 64-camera ring, "
+                     "one camera per GPU per step"),
+    "cfg3_r4": ("cfg3_r4", "BASELINE configs[2] at -r 4: 3M 6-D primitives, 1245x825"),
+    "cfg2": ("cfg2", "BASELINE configs[1]: 300k 6-D primitives, 800x800, white background"),
+    "cfg1": ("cfg1", "BASELINE configs[0]: 100k 6-D primitives, 800x800"),
+    "cfg4": ("cfg4", "BASELINE configs[3]: 1M 7-D primitives, 1352x1014, 300 timestamps"),
+}
+N_RING = 64
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # pragma: no cover
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # pragma: no cover
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_workload(name, n_override=None):
+    from ubs_b200 import synth
+
+    cfg_name, desc = WORKLOADS[name]
+    scene, cams, bg, cfg = synth.make_config(cfg_name, n_override=n_override, cams_override=N_RING)
+    return scene, cams, bg, cfg, desc
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the reference arm: CPU oracle port on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_oracle_pass(scene, cam, bg, backward):
+    """One frame through the CPU restatement of the reference path (oracle/): returns seconds."""
+    from oracle import ubs_oracle as O
+
+    t0 = time.perf_counter()
+    if backward:
+        params = [t.clone().requires_grad_(True) for t in scene.tensors()]
+        rc, ra, _ = O.render(params, cam.viewmat, cam.K, cam.cam_pos, cam.timestamp, cam.width, cam.height, bg)
+        P = cam.width * cam.height
+        g = torch.Generator().manual_seed(1)
+        torch.autograd.backward((rc, ra), (torch.randn(rc.shape, generator=g) / P, torch.zeros_like(ra)))
+    else:
+        with torch.no_grad():
+            O.render(scene.tensors(), cam.viewmat, cam.K, cam.cam_pos, cam.timestamp, cam.width, cam.height, bg)
+    return time.perf_counter() - t0
+
+
+def run_reference_cpu(args, rank, world):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    scene, cams, bg, cfg, desc = make_workload(args.workload)
+    from oracle import ubs_oracle as O
+
+    O.build()
+    for w in range(min(args.warmup, 1)):
+        cpu_oracle_pass(scene, cams[w % N_RING], bg, False)
+    steps = max(1, min(args.steps, 5))  # bounded sample: each step is one whole frame, ~4 s on 8 cores
+    times = [cpu_oracle_pass(scene, cams[(k + 1) % N_RING], bg, False) for k in range(steps)]
+    t_bwd = cpu_oracle_pass(scene, cams[0], bg, True)
+    fps = steps / sum(times)
+    cores = os.cpu_count() or 1
+    sample = "%d whole frames of the same workload (forward), 1 forward+backward frame" % steps
+    line = {
+        "impl": "reference", "metric": "render_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": 0,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * sum(times) / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "name": args.workload, "N": scene.N, "D": scene.D, "width": cfg["width"],
+                   "height": cfg["height"]},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                         "train_it_per_s": 1.0 / t_bwd},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "train": {"value": 1.0 / t_bwd, "unit": "it/s", "ms_per_step": 1e3 * t_bwd},
+        "note": "the reference's path is CUDA-only past projection (its torch rasteriser needs CUDA + nerfacc); "
+                "this arm is the CPU restatement in oracle/ (torch per-primitive stages + C/OpenMP tile/compositing)",
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# extra arm: the reference's own CUDA kernels on the same GPU (the number to beat)
+# ----------------------------------------------------------------------------------------------------------------
+def run_reference_cuda(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import ref_cuda as ref
+
+    if not ref.available():
+        print(json.dumps({"impl": "reference_cuda", "unavailable": "oracle/_ref/ubs_ref_cuda.so not built"}))
+        return
+    dev = "cuda:0"
+    scene, cams, bg, cfg, desc = make_workload(args.workload)
+    scene = scene.to(dev)
+    bg = bg.to(dev)
+    from ubs_b200 import synth
+
+    cams = [synth.Camera(c.viewmat.to(dev), c.K.to(dev), c.cam_pos.to(dev), c.width, c.height, c.timestamp)
+            for c in cams]
+    W, H = cfg["width"], cfg["height"]
+    P = W * H
+
+    def fwd(k):
+        cam = cams[k % N_RING]
+        m, v, o, b0 = ref.condition(scene, cam)
+        return ref.rasterization_fwd(m, v, o, b0, scene.rgb, cam.viewmat[None], cam.K[None], W, H,
+                                     backgrounds=bg[None])
+
+    v_rc = torch.randn(1, H, W, 3, device=dev) / P
+    v_ra = torch.zeros(1, H, W, 1, device=dev)
+
+    def train(k):
+        ref.chain_grads(scene, cams[k % N_RING], bg, v_rc, v_ra)
+
+    out = {}
+    for name, fn in (("render", fwd), ("train", train)):
+        for w in range(args.warmup):
+            fn(w)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(args.steps):
+            fn(args.warmup + k)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / args.steps
+    line = {"impl": "reference_cuda", "metric": "render_frames_per_s", "value": 1e3 / out["render"],
+            "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": out["render"], "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "name": args.workload},
+            "train": {"value": 1e3 / out["train"], "unit": "it/s", "ms_per_step": out["train"]},
+            "note": "reference gsplat CUDA kernels recompiled for sm_100a (oracle/_ref), driven as "
+                    "scene/beta_model.py:660-711 drives them, on the same GPU"}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# this library
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+
+    from ubs_b200 import _lib, fused, parallel
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    scene, cams, bg, cfg, desc = make_workload(args.workload)
+    W, H, D, N = cfg["width"], cfg["height"], scene.D, scene.N
+    P = W * H
+    rec = fused.pack_records(D, *[t.to(dev) for t in scene.tensors()])
+    V = torch.stack([c.viewmat for c in cams]).to(dev)
+    K = torch.stack([c.K for c in cams]).to(dev)
+    Cp = torch.stack([c.cam_pos for c in cams]).to(dev)
+    Ts = torch.tensor([c.timestamp for c in cams], device=dev) if D == 7 else None
+    bgd = bg[None].to(dev)
+    rz = fused.FusedRasterizer(D, N, W, H, n_cams=1, device=dev)
+    rz.enable_stage_timing(False)
+
+    def cam_of(step):
+        return (step * world + rank) % N_RING
+
+    def render(step):
+        c = cam_of(step)
+        return rz.forward(rec, V[c:c + 1], K[c:c + 1], Cp[c:c + 1], None if Ts is None else Ts[c:c + 1], bgd)
+
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    v_rc = torch.randn(1, H, W, 3, device=dev, generator=g) / P
+    v_ra = torch.zeros(1, H, W, 1, device=dev)
+    v_rec = torch.empty_like(rec)
+    trainer = parallel.DataParallelTrainer(rz, world)
+
+    def train(step):
+        c = cam_of(step)
+        trainer.step(rec, V[c:c + 1], K[c:c + 1], Cp[c:c + 1], None if Ts is None else Ts[c:c + 1], bgd, v_rc, v_ra,
+                     v_rec)
+
+    def timed(fn, steps, warmup, with_stages):
+        for w in range(warmup):
+            fn(w)
+        barrier()
+        rz.enable_stage_timing(with_stages)
+        sampler = ClockSampler(physical_gpu_index(local_rank))
+        sampler.start()
+        n0 = lib.ubs_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            fn(warmup + k)
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        launches = lib.ubs_launch_count() - n0
+        ms = e0.elapsed_time(e1)
+        stages = rz.stage_times_ms() if with_stages else {}
+        rz.enable_stage_timing(False)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches, clocks, stages
+
+    # ---- value: frames/s, inputs resident in HBM --------------------------------------------------------------
+    ms_render, launches, clocks, stages = timed(render, args.steps, args.warmup, True)
+    fps = world * args.steps / (ms_render / 1e3)
+    # work counters over a few cameras of the ring (diagnostic kernel, outside the timed region)
+    counts = None
+    for k in range(0, min(args.steps, 8)):
+        render(args.warmup + k)
+        c = rz.work_counts()
+        counts = c if counts is None else {kk: counts[kk] + c[kk] for kk in c}
+    n_cnt = min(args.steps, 8)
+    counts = {kk: v / n_cnt for kk, v in counts.items()}
+
+    # ---- train it/s: forward + backward (+ NCCL allreduce of the gradient records when world > 1) ---------------
+    ms_train, launches_train, clocks_train, stages_train = timed(train, args.steps, args.warmup, True)
+    its = world * args.steps / (ms_train / 1e3)
+
+    # ---- e2e: host buffers in, host image out, through the public API -----------------------------------------
+    h_cam = torch.empty((N_RING, 16 + 9 + 3 + 1), dtype=torch.float32).pin_memory()
+    h_cam[:, :16] = torch.stack([c.viewmat for c in cams]).reshape(N_RING, 16)
+    h_cam[:, 16:25] = torch.stack([c.K for c in cams]).reshape(N_RING, 9)
+    h_cam[:, 25:28] = torch.stack([c.cam_pos for c in cams])
+    h_cam[:, 28] = torch.tensor([c.timestamp for c in cams])
+    pipe = fused.HostPipeline(rz, depth=2)
+
+    def e2e(step):
+        pipe.render_to_host(rec, h_cam[cam_of(step)], bgd)
+
+    for w in range(args.warmup):
+        e2e(w)
+    pipe.drain()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e2e(args.warmup + k)
+    pipe.drain()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = t.item()
+    e2e_fps = world * args.steps / t_e2e
+    h2d = h_cam[0].numel() * 4
+    d2h = P * 4 * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (compositing forward) + the HBM-bound stages -------------------------
+    hbm_peak, peak_src = measured_peaks()
+    sm_count = lib.ubs_device_sm_count()
+    clk = (clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965) * 1e6
+    fp32_peak = sm_count * 128 * clk / 1e12  # T lane-instructions/s at the clock observed during the run
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    rast_ms = stages.get("rasterize_fwd", (0, float("nan")))[1]
+    slots = 9.0 * counts["E_cull"] + 11.0 * counts["E_acc"]
+    slots_ref = 9.0 * counts["E_test"] + 11.0 * counts["E_acc"]
+    achieved = slots / (rast_ms * 1e-3) / 1e12
+    roofline = {
+        "kernel": "rasterize_fwd_kernel<3>", "bound": "fp32", "achieved": achieved, "peak": fp32_peak,
+        "unit": "Tinstr/s", "frac": achieved / fp32_peak, "traffic": traffic.get("rasterize_fwd_kernel"),
+        "ms_per_launch": rast_ms,
+        "achieved_reference_algorithm": slots_ref / (rast_ms * 1e-3) / 1e12,
+        "note": "FP32 issue-slot roofline (no dense contraction -> no tensor cores): slots = 9*E_cull + 11*E_acc "
+                "(SURVEY 8(d) per-evaluation costs x evaluations left after the sub-tile cull); peak = SMs x 128 "
+                "lanes x observed SM clock; achieved_reference_algorithm uses E_test (no cull) instead",
+    }
+    vis, pairs = counts["visible"], counts["pairs"]
+    rec_b = rec.shape[1] * 4
+    key_bits = 32 + max(1, (rz.tw * rz.th).bit_length()) + 1
+    passes = (key_bits + 7) // 8
+    stage_roof = {}
+
+    def hbm_stage(name, ms, nbytes):
+        if ms == ms and ms > 0:
+            a = nbytes / (ms * 1e-3) / 1e9
+            stage_roof[name] = {"bound": "hbm", "ms": ms, "algorithmic_bytes": nbytes, "achieved": a, "peak": hbm_peak,
+                                "unit": "GB/s", "frac": a / hbm_peak, "traffic": traffic.get(name)}
+
+    hbm_stage("fused_project_fwd", stages.get("fused_project_fwd", (0, float("nan")))[1], N * rec_b + vis * 36)
+    hbm_stage("isect_emit_sort_offsets", stages.get("isect_emit_sort_offsets", (0, float("nan")))[1],
+              pairs * (12 + 8 + 24 * passes + 8))
+    hbm_stage("fused_project_bwd", stages_train.get("fused_project_bwd", (0, float("nan")))[1],
+              2 * N * rec_b + vis * 76)
+    stage_roof["rasterize_bwd"] = {"bound": "fp32", "ms": stages_train.get("rasterize_bwd", (0, float("nan")))[1],
+                                   "slots": 9.0 * counts["E_cull"] + 45.0 * counts["E_acc"]}
+    rb = stage_roof["rasterize_bwd"]
+    if rb["ms"] == rb["ms"] and rb["ms"] > 0:
+        rb["achieved"] = rb["slots"] / (rb["ms"] * 1e-3) / 1e12
+        rb["peak"], rb["unit"], rb["frac"] = fp32_peak, "Tinstr/s", rb["slots"] / (rb["ms"] * 1e-3) / 1e12 / fp32_peak
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample --------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu_oracle_pass(scene, cams[0], bg, False)  # warm-up (builds / loads the C oracle, faults the pages)
+        t_f = [cpu_oracle_pass(scene, cams[k + 1], bg, False) for k in range(2)]
+        t_b = cpu_oracle_pass(scene, cams[3], bg, True)
+        cpu = {"value": len(t_f) / sum(t_f), "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "2 whole forward frames + 1 forward+backward frame of the same workload (oracle/, "
+                         "torch + C/OpenMP on all host cores)",
+               "train_it_per_s": 1.0 / t_b}
+
+    line = {
+        "metric": "render_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_render / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "name": args.workload, "N": N, "D": D, "width": W, "height": H,
+                   "cameras_per_gpu_per_step": 1, "parallelism": "camera-parallel x%d, no collective" % world,
+                   "l2": "inputs larger than L2 (%.0f MB parameter records re-read every step)" % (N * rec_b / 1e6),
+                   "pairs_per_frame": pairs, "visible_per_frame": vis, "peak_source": peak_src},
+        "train": {"metric": "train_it_per_s", "value": its, "unit": "it/s", "ms_per_step": ms_train / args.steps,
+                  "what": "forward + backward to the packed parameter-gradient records" +
+                          (" + NCCL allreduce(sum) of the %.0f MB gradient buffer" % (N * rec_b / 1e6)
+                           if world > 1 else ""),
+                  "gpu_launches": launches_train, "clocks": clocks_train,
+                  "stages_ms": {k: v[1] for k, v in stages_train.items()}},
+        "roofline": roofline, "stages": stage_roof, "stages_ms": {k: v[1] for k, v in stages.items()},
+        "work": counts, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "what": "fused.HostPipeline.render_to_host: pinned host camera -> device, render, RGBA image -> "
+                        "pinned host, double-buffered; wall clock over the timed steps"},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_cuda"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_cpu(args, rank, world)
+    elif args.impl == "reference_cuda":
+        run_reference_cuda(args, rank, world)
+    else:
+        if world == 1 and args.gpus > 1:
+            sys.stderr.write("bench.py: --gpus %d without torchrun: running 1 rank\n" % args.gpus)
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

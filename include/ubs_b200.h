@@ -34,6 +34,7 @@ extern "C" {
 
 /* ---- library ------------------------------------------------------------------------------------------ */
 const char *ubs_last_error(void);
+unsigned long long ubs_launch_count(void); /* kernels launched by this library in this process (bench bookkeeping) */
 int ubs_version(void);           /* ABI version, bumped on any signature change                          */
 int ubs_device_sm_count(void);   /* multiProcessorCount of the current device (grid sizing), <0 on error */
 
@@ -169,6 +170,13 @@ int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_c
                       /* gradients, ACCUMULATED into (caller zero-fills): */
                       float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, float *v_betas,
                       void *stream);
+
+/* Diagnostic work counters for the compositing roofline (no reference counterpart):
+ * counts[4] (device u64) = { E_test, E_acc, E_cull, pairs staged } -- see csrc/rasterize_fwd.cu.              */
+int ubs_rasterize_count(int C, const int64_t *n_isects, int64_t isect_capacity, const float *means2d,
+                        const float *conics, const float *opacities, const float *betas, int width, int height,
+                        int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
+                        unsigned long long *counts, void *stream);
 
 /* ---- fused fast path: raw parameters -> screen-space records ------------------------------------------- */
 /* New entry (no single reference counterpart): fuses the activations (scene/beta_model.py:36-52,103-121),

@@ -98,3 +98,52 @@ def rasterization_fwd(means, covars3x3, opacities, betas, colors, viewmats, Ks, 
     return dict(radii=radii, means2d=means2d, depths=depths, conics=conics, compensations=comps, opacities=opac,
                 betas=bet, colors=cols, tiles_per_gauss=tiles_per_gauss, isect_ids=isect_ids, flatten_ids=flatten_ids,
                 isect_offsets=offsets, render_colors=rc, render_alphas=ra, last_ids=last_ids)
+
+
+def chain_grads(scene, cam, bg, v_rc, v_ra, keep=None):
+    """Gradients of the 7 raw parameter tensors through the reference kernels + torch glue, restating the autograd
+    graph of scene/beta_model.py:660-711 with explicit VJP calls (cuda/_wrapper.py:573-684,807-1050)."""
+    C_ = load()
+    D = scene.D
+    W, H = cam.width, cam.height
+    raw = [t.detach().clone().requires_grad_(True) for t in scene.tensors()]
+    xyz, mean, rgb, opacity, beta, scale, ltri = raw
+    s_act = torch.nn.functional.softplus(scale)
+    o_act = torch.sigmoid(opacity)
+    b_act = 4.0 * torch.exp(beta)
+    mu = torch.cat([xyz, mean], dim=-1)
+    ri, rj = tril_rest(D, "cuda")
+    with torch.no_grad():
+        l3 = ltri[:, :3].contiguous()
+        rot = C_.l_triangle_to_rotmat_fwd(l3)
+        covar = C_.rot_scale_l_triangle_to_covar_fwd(rot, s_act.contiguous(), ltri.contiguous(), ri, rj, False)
+        q = query_for(scene, cam).contiguous()
+        bc = b_act[:, 1:].contiguous()
+        m3, v3, o3 = C_.cond_mean_convariance_opacity_fwd(mu.contiguous(), covar, o_act.contiguous(), bc, q)
+        R = rasterization_fwd(m3, v3, o3.squeeze(-1), b_act[:, 0].contiguous(), rgb, cam.viewmat[None], cam.K[None],
+                                  W, H, backgrounds=bg[None])
+        g2d, gcon, gcol, gop, gbe = C_.rasterize_to_pixels_bwd(
+            R["means2d"], R["conics"], R["colors"], R["opacities"], R["betas"], bg[None], None, W, H, 16,
+            R["isect_offsets"], R["flatten_ids"], R["render_alphas"], R["last_ids"], v_rc, v_ra)
+        tri = ([0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2])
+        cov6 = v3[..., tri[0], tri[1]].contiguous()
+        g_m3, g_cov6, _, _, _ = C_.fully_fused_projection_bwd(
+            m3, cov6, None, None, cam.viewmat[None], cam.K[None], W, H, 0.3, False, R["radii"], R["conics"], None, g2d,
+            torch.zeros_like(R["depths"]), gcon, None, False)
+        g_v3 = torch.zeros_like(v3)
+        g_v3[:, tri[0], tri[1]] = g_cov6
+        g_mu, g_covar, g_o, g_bc = C_.cond_mean_convariance_opacity_bwd(
+            mu.contiguous(), covar, o_act.contiguous(), bc, q, g_m3, g_v3.contiguous(), gop[0][:, None].contiguous())
+        g_rot, g_s, g_lt = C_.rot_scale_l_triangle_to_covar_bwd(rot, s_act.contiguous(), ltri.contiguous(), ri, rj,
+                                                               False, g_covar)
+        g_l3 = C_.l_triangle_to_rotmat_bwd(l3, g_rot)
+        g_lt = g_lt.clone()
+        g_lt[:, :3] += g_l3
+        g_b = torch.cat([gbe[0][:, None], g_bc], dim=-1)
+        if keep is not None:  # intermediate results for the golden fixtures
+            keep.update(cond_means=m3, cond_covars=v3, cond_opac=o3, v_means2d=g2d, v_conics=gcon, v_colors=gcol,
+                        v_opacities=gop, v_betas=gbe, v_cond_means=g_m3, v_cond_cov6=g_cov6, v_mu=g_mu,
+                        v_covar=g_covar, v_opac_act=g_o, v_beta_cond=g_bc, v_scale_act=g_s, v_rot=g_rot)
+    # torch glue backward (activations, cat)
+    torch.autograd.backward([s_act, o_act, b_act, mu], [g_s, g_o, g_b, g_mu])
+    return [xyz.grad, mean.grad, gcol[0], opacity.grad, beta.grad, scale.grad, g_lt], R

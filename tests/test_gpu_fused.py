@@ -92,51 +92,6 @@ def test_fused_capacity_overflow_is_flagged_and_recovers():
     assert torch.equal(rc, rc2) and torch.equal(ra, ra2)
 
 
-def _reference_chain_grads(ref, scene, cam, bg, v_rc, v_ra):
-    """Gradients of the 7 raw parameter tensors through the reference kernels + torch glue, restating the autograd
-    graph of scene/beta_model.py:660-711 with explicit VJP calls (cuda/_wrapper.py:573-684,807-1050)."""
-    C_ = ref.load()
-    D = scene.D
-    W, H = cam.width, cam.height
-    raw = [t.detach().clone().requires_grad_(True) for t in scene.tensors()]
-    xyz, mean, rgb, opacity, beta, scale, ltri = raw
-    s_act = torch.nn.functional.softplus(scale)
-    o_act = torch.sigmoid(opacity)
-    b_act = 4.0 * torch.exp(beta)
-    mu = torch.cat([xyz, mean], dim=-1)
-    ri, rj = ref.tril_rest(D, "cuda")
-    with torch.no_grad():
-        l3 = ltri[:, :3].contiguous()
-        rot = C_.l_triangle_to_rotmat_fwd(l3)
-        covar = C_.rot_scale_l_triangle_to_covar_fwd(rot, s_act.contiguous(), ltri.contiguous(), ri, rj, False)
-        q = ref.query_for(scene, cam).contiguous()
-        bc = b_act[:, 1:].contiguous()
-        m3, v3, o3 = C_.cond_mean_convariance_opacity_fwd(mu.contiguous(), covar, o_act.contiguous(), bc, q)
-        R = ref.rasterization_fwd(m3, v3, o3.squeeze(-1), b_act[:, 0].contiguous(), rgb, cam.viewmat[None], cam.K[None],
-                                  W, H, backgrounds=bg[None])
-        g2d, gcon, gcol, gop, gbe = C_.rasterize_to_pixels_bwd(
-            R["means2d"], R["conics"], R["colors"], R["opacities"], R["betas"], bg[None], None, W, H, 16,
-            R["isect_offsets"], R["flatten_ids"], R["render_alphas"], R["last_ids"], v_rc, v_ra)
-        tri = ([0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2])
-        cov6 = v3[..., tri[0], tri[1]].contiguous()
-        g_m3, g_cov6, _, _, _ = C_.fully_fused_projection_bwd(
-            m3, cov6, None, None, cam.viewmat[None], cam.K[None], W, H, 0.3, False, R["radii"], R["conics"], None, g2d,
-            torch.zeros_like(R["depths"]), gcon, None, False)
-        g_v3 = torch.zeros_like(v3)
-        g_v3[:, tri[0], tri[1]] = g_cov6
-        g_mu, g_covar, g_o, g_bc = C_.cond_mean_convariance_opacity_bwd(
-            mu.contiguous(), covar, o_act.contiguous(), bc, q, g_m3, g_v3.contiguous(), gop[0][:, None].contiguous())
-        g_rot, g_s, g_lt = C_.rot_scale_l_triangle_to_covar_bwd(rot, s_act.contiguous(), ltri.contiguous(), ri, rj,
-                                                               False, g_covar)
-        g_l3 = C_.l_triangle_to_rotmat_bwd(l3, g_rot)
-        g_lt = g_lt.clone()
-        g_lt[:, :3] += g_l3
-        g_b = torch.cat([gbe[0][:, None], g_bc], dim=-1)
-    # torch glue backward (activations, cat)
-    torch.autograd.backward([s_act, o_act, b_act, mu], [g_s, g_o, g_b, g_mu])
-    return [xyz.grad, mean.grad, gcol[0], opacity.grad, beta.grad, scale.grad, g_lt], R
-
-
 @pytest.mark.parametrize("D,N,W,H", [(6, 50000, 480, 360), (7, 30000, 400, 300)])
 def test_fused_backward_matches_reference_chain(D, N, W, H):
     ref = _ref()
@@ -149,7 +104,7 @@ def test_fused_backward_matches_reference_chain(D, N, W, H):
     g = torch.Generator(device="cuda").manual_seed(5)
     v_rc = torch.randn(1, H, W, 3, device="cuda", generator=g) / (H * W)
     v_ra = torch.randn(1, H, W, 1, device="cuda", generator=g) / (H * W)
-    ref_grads, R = _reference_chain_grads(ref, scene, cam, bg, v_rc, v_ra)
+    ref_grads, R = ref.chain_grads(scene, cam, bg, v_rc, v_ra)
 
     rec = fused.pack_records(D, *scene.tensors()).requires_grad_(True)
     rz = fused.FusedRasterizer(D, N, W, H, n_cams=1)

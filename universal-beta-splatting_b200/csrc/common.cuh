@@ -9,6 +9,7 @@
 namespace ubs {
 
 void set_error(const char *fmt, ...);
+void count_launch();  // bumps the process-wide kernel-launch counter (ubs_launch_count)
 
 #define UBS_CHECK_ARG(cond, ...)                                                                                       \
     do {                                                                                                               \
@@ -29,6 +30,7 @@ void set_error(const char *fmt, ...);
 
 #define UBS_LAUNCH_CHECK(name)                                                                                         \
     do {                                                                                                               \
+        ::ubs::count_launch();                                                                                         \
         cudaError_t _e = cudaGetLastError();                                                                           \
         if (_e != cudaSuccess) {                                                                                       \
             ::ubs::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));                                 \

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ubs {
@@ -12,8 +14,11 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace ubs
 
+extern "C" unsigned long long ubs_launch_count(void) { return ubs::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char *ubs_last_error(void) { return ubs::g_err; }
 extern "C" int ubs_version(void) { return 1; }
 extern "C" int ubs_device_sm_count(void) {

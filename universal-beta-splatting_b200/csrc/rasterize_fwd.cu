@@ -148,6 +148,81 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
     }
 }
 
+
+// Diagnostic (not on the hot path): work counters for the roofline bookkeeping of SURVEY.md 8(d).
+//   counts[0] = E_test: (pixel, pair) evaluations the reference algorithm performs (every pair of the tile list
+//               until the pixel is done, rasterize_to_pixels_fwd.cu:135-173)
+//   counts[1] = E_acc : evaluations that pass the sigma test (alpha is computed)
+//   counts[2] = E_cull: evaluations left after this library's per-warp 8x4 sub-tile cull (what it executes)
+//   counts[3] = pairs staged: 256-pair batches loaded until the whole tile is done, in pairs
+__global__ void __launch_bounds__(kTilePixels)
+rasterize_count_kernel(int C, const int64_t *__restrict__ n_isects_dev, int64_t isect_capacity,
+                       const float2 *__restrict__ means2d, const float *__restrict__ conics,
+                       const float *__restrict__ opacities, const float *__restrict__ betas, uint32_t width,
+                       uint32_t height, uint32_t tile_width, uint32_t tile_height,
+                       const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
+                       unsigned long long *__restrict__ counts) {
+    const uint32_t cam = blockIdx.z;
+    const uint32_t tile_id = blockIdx.y * tile_width + blockIdx.x;
+    const uint32_t tr = threadIdx.x;
+    const SubTile st = sub_tile_of(tr);
+    const uint32_t i = blockIdx.y * kTile + st.py, j = blockIdx.x * kTile + st.px;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const bool inside = (i < height && j < width);
+    tile_offsets += (size_t)cam * tile_height * tile_width;
+    const int64_t n_isects = min(*n_isects_dev, isect_capacity);
+    const int32_t range_start = tile_offsets[tile_id];
+    const int32_t range_end = (cam == (uint32_t)C - 1 && tile_id == tile_width * tile_height - 1)
+                                  ? (int32_t)n_isects
+                                  : tile_offsets[tile_id + 1];
+    const float wx0 = (float)(blockIdx.x * kTile + st.bx * kSubW) + 0.5f, wx1 = wx0 + (float)(kSubW - 1);
+    const float wy0 = (float)(blockIdx.y * kTile + st.by * kSubH) + 0.5f, wy1 = wy0 + (float)(kSubH - 1);
+    unsigned long long n_test = 0, n_acc = 0, n_cull = 0;
+    int32_t stop = range_start;  // one past the last pair this pixel looks at
+    if (inside) {
+        float T = 1.f;
+        stop = range_end;
+        for (int32_t idx = range_start; idx < range_end; ++idx) {
+            const int32_t g = flatten_ids[idx];
+            const float2 xy = means2d[g];
+            const float a = conics[(size_t)g * 3], b = conics[(size_t)g * 3 + 1], c = conics[(size_t)g * 3 + 2];
+            ++n_test;
+            const float4 bb = support_bbox(xy.x, xy.y, a, b, c);
+            if ((bb.x <= wx1) && (bb.y >= wx0) && (bb.z <= wy1) && (bb.w >= wy0)) ++n_cull;
+            const float dx = xy.x - px, dy = xy.y - py;
+            const float sigma = (a * dx * dx + c * dy * dy) + 2.f * b * dx * dy;
+            if (sigma < 0.f || sigma >= 1.f) continue;
+            ++n_acc;
+            const float alpha = fminf(0.999f, opacities[g] * __powf(1.f - sigma, betas[g]));
+            const float next_T = T * (1.f - alpha);
+            if (next_T <= 1e-4f) {
+                stop = idx + 1;
+                break;
+            }
+            T = next_T;
+        }
+    }
+    __shared__ unsigned long long s_cnt[3];
+    __shared__ int32_t s_stop;
+    if (tr == 0) {
+        s_cnt[0] = s_cnt[1] = s_cnt[2] = 0ull;
+        s_stop = range_start;
+    }
+    __syncthreads();
+    atomicAdd(&s_cnt[0], n_test);
+    atomicAdd(&s_cnt[1], n_acc);
+    atomicAdd(&s_cnt[2], n_cull);
+    atomicMax(&s_stop, stop);
+    __syncthreads();
+    if (tr == 0) {
+        atomicAdd(counts + 0, s_cnt[0]);
+        atomicAdd(counts + 1, s_cnt[1]);
+        atomicAdd(counts + 2, s_cnt[2]);
+        const int32_t staged = min(range_end - range_start, (s_stop - range_start + kTilePixels - 1) / kTilePixels * kTilePixels);
+        atomicAdd(counts + 3, (unsigned long long)max(staged, 0));
+    }
+}
+
 template <int CH>
 int launch_fwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const float *means2d, const float *conics,
                const float *colors, const float *opacities, const float *betas, const float *backgrounds,
@@ -198,4 +273,22 @@ extern "C" int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, int6
             return UBS_EUNSUPPORTED;
     }
 #undef UBS_FWD_CASE
+}
+
+extern "C" int ubs_rasterize_count(int C, const int64_t *n_isects, int64_t isect_capacity, const float *means2d,
+                                   const float *conics, const float *opacities, const float *betas, int width,
+                                   int height, int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
+                                   unsigned long long *counts, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(C > 0 && width > 0 && height > 0 && tile_size == kTile, "rasterize_count: bad sizes");
+    UBS_CHECK_ARG(n_isects && means2d && conics && opacities && betas && offsets && flatten_ids && counts,
+                  "rasterize_count: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    UBS_CUDA_TRY(cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), s));
+    const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
+    rasterize_count_kernel<<<dim3(tw, th, (unsigned)C), kTilePixels, 0, s>>>(
+        C, n_isects, isect_capacity, (const float2 *)means2d, conics, opacities, betas, (uint32_t)width,
+        (uint32_t)height, tw, th, offsets, flatten_ids, counts);
+    UBS_LAUNCH_CHECK("rasterize_count_kernel");
+    return UBS_OK;
 }

@@ -15,6 +15,7 @@ _P = c_void_p  # every device pointer crosses the ABI as an opaque address
 # name -> (restype, argtypes); must list every symbol of include/ubs_b200.h
 SIGNATURES = {
     "ubs_last_error": (c_char_p, []),
+    "ubs_launch_count": (ctypes.c_ulonglong, []),
     "ubs_version": (c_int, []),
     "ubs_device_sm_count": (c_int, []),
     "ubs_record_stride": (c_int, [c_int]),
@@ -38,6 +39,7 @@ SIGNATURES = {
                                   _P, _P, _P, _P]),
     "ubs_rasterize_bwd": (c_int, [c_int, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int] +
                           [_P] * 12),
+    "ubs_rasterize_count": (c_int, [c_int, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "ubs_fused_project_fwd": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_float,
                                       c_float, c_float, c_int, c_int, c_int, c_int] + [_P] * 10 + [c_size_t, _P]),
     "ubs_fused_project_bwd": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_int] +

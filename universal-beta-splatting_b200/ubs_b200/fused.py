@@ -47,6 +47,25 @@ def unpack_records(D, rec: Tensor):
     return tuple(rec[:, sl[n]] for n in ("xyz", "mean", "rgb", "opacity", "beta", "scale", "l_triangle"))
 
 
+class _StageTimer:
+    """Records a CUDA-event pair around a stage on the current stream when stage timing is enabled."""
+
+    def __init__(self, sink, name):
+        self.sink, self.name = sink, name
+
+    def __enter__(self):
+        if self.sink is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.sink is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.sink.setdefault(self.name, []).append((self.e0, e1))
+        return False
+
+
 class FusedRasterizer:
     """Persistent buffers + the launch sequence fused-project -> emit/sort/offsets -> composite.
 
@@ -84,7 +103,32 @@ class FusedRasterizer:
         self._host_count = torch.zeros((2,), dtype=torch.int64).pin_memory()
         self._count_event = None
         self._alloc_pairs(capacity if capacity is not None else max(8 * C * N, 1 << 16))
-        self.launches_per_frame = 0
+        self.stage_events = None  # dict stage -> [(start, end)] when enable_stage_timing() was called
+
+    # ---- optional per-stage CUDA-event timing (bench.py's roofline bookkeeping) --------------------------------
+    def enable_stage_timing(self, on: bool = True):
+        self.stage_events = {} if on else None
+
+    def _stage(self, name: str):
+        return _StageTimer(self.stage_events, name)
+
+    def stage_times_ms(self):
+        """{stage: (launch count, mean ms)} over everything recorded since enable_stage_timing(); synchronises."""
+        torch.cuda.synchronize(self.device)
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1))
+                for k, v in (self.stage_events or {}).items()}
+
+    def work_counts(self):
+        """Compositing work counters of the most recent forward() (diagnostic kernel):
+        dict(E_test, E_acc, E_cull, pairs_staged, pairs, visible)."""
+        counts = torch.zeros((4,), dtype=torch.int64, device=self.device)
+        check(self.lib.ubs_rasterize_count(
+            self.C, ptr(self.n_isects), self.capacity, ptr(self.means2d), ptr(self.conics), ptr(self.opacities),
+            ptr(self.betas), self.W, self.H, self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(counts),
+            torch.cuda.current_stream().cuda_stream), "ubs_rasterize_count")
+        c = counts.tolist()
+        return dict(E_test=c[0], E_acc=c[1], E_cull=c[2], pairs_staged=c[3], pairs=self.last_pair_count(),
+                    visible=int((self.radii > 0).sum()))
 
     def _alloc_pairs(self, capacity: int):
         self.capacity = int(capacity)
@@ -113,37 +157,44 @@ class FusedRasterizer:
     @torch.no_grad()
     def forward(self, records: Tensor, viewmats: Tensor, Ks: Tensor, cam_pos: Tensor,
                 timestamps: Optional[Tensor] = None, backgrounds: Optional[Tensor] = None,
-                prim_mask: Optional[Tensor] = None):
+                prim_mask: Optional[Tensor] = None, out=None):
         """records [N,stride], viewmats [C,4,4], Ks [C,3,3], cam_pos [C,3], timestamps [C] (D=7),
-        backgrounds [C,3] -> (render_colors [C,H,W,3], render_alphas [C,H,W,1]) (buffers owned by self)."""
+        backgrounds [C,3] -> (render_colors [C,H,W,3], render_alphas [C,H,W,1]).  The images land in buffers owned
+        by self, or in `out` = (colors, alphas) when given (backward() needs the default buffers)."""
         lib, s = self.lib, torch.cuda.current_stream().cuda_stream
         C, N, D = self.C, self.N, self.D
         assert records.shape == (N, record_stride(D)) and records.is_cuda and records.dtype == torch.float32
         assert records.is_contiguous()
         assert viewmats.shape == (C, 4, 4) and Ks.shape == (C, 3, 3) and cam_pos.shape == (C, 3)
         self._poll_count()
+        rc_out, ra_out = (self.render_colors, self.render_alphas) if out is None else out
+        assert rc_out.shape == self.render_colors.shape and ra_out.shape == self.render_alphas.shape
+        assert rc_out.is_contiguous() and ra_out.is_contiguous() and rc_out.dtype == torch.float32
         mask_u8 = None if prim_mask is None else prim_mask.to(torch.bool).contiguous().view(torch.uint8)
-        check(lib.ubs_fused_project_fwd(
+        with self._stage("fused_project_fwd"):
+          check(lib.ubs_fused_project_fwd(
             C, N, D, ptr(records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), ptr(mask_u8), self.W, self.H,
             self.eps2d, self.near, self.far, self.clip, 1 if self.aa else 0, self.tile_size, self.tw, self.th,
             ptr(self.radii), ptr(self.means2d), ptr(self.depths), ptr(self.conics), ptr(self.opacities),
             ptr(self.betas), ptr(self.colors), ptr(self.tiles_per_gauss), ptr(self.n_isects), ptr(self.workspace),
             self.workspace.numel(), s), "ubs_fused_project_fwd")
-        check(lib.ubs_isect_emit_sort(
+        with self._stage("isect_emit_sort_offsets"):
+          check(lib.ubs_isect_emit_sort(
             C, N, ptr(self.means2d), ptr(self.radii), ptr(self.depths), self.tile_size, self.tw, self.th, 1,
             ptr(self.tiles_per_gauss), ptr(self.n_isects), self.capacity, ptr(self.isect_ids), ptr(self.flatten_ids),
             ptr(self.offsets), ptr(self.status), ptr(self.workspace), self.workspace.numel(), s), "ubs_isect_emit_sort")
-        check(lib.ubs_rasterize_fwd(
+        with self._stage("rasterize_fwd"):
+          check(lib.ubs_rasterize_fwd(
             C, N, ptr(self.n_isects), self.capacity, ptr(self.means2d), ptr(self.conics), ptr(self.colors),
             ptr(self.opacities),
             ptr(self.betas), ptr(backgrounds), None, 3, self.W, self.H, self.tile_size, ptr(self.offsets),
-            ptr(self.flatten_ids), ptr(self.render_colors), ptr(self.render_alphas), ptr(self.last_ids), s),
+            ptr(self.flatten_ids), ptr(rc_out), ptr(ra_out), ptr(self.last_ids), s),
             "ubs_rasterize_fwd")
         if self._count_event is None:
             self._host_count[0:1].copy_(self.n_isects, non_blocking=True)
             self._count_event = torch.cuda.Event()
             self._count_event.record()
-        return self.render_colors, self.render_alphas
+        return rc_out, ra_out
 
     def _grad_buffers(self):
         if getattr(self, "_gflat", None) is None:
@@ -169,7 +220,8 @@ class FusedRasterizer:
         v_rc = v_render_colors.contiguous()
         v_ra = v_render_alphas.contiguous()
         assert v_rc.shape == (C, self.H, self.W, 3) and v_ra.shape == (C, self.H, self.W, 1)
-        check(lib.ubs_rasterize_bwd(
+        with self._stage("rasterize_bwd"):
+          check(lib.ubs_rasterize_bwd(
             C, N, ptr(self.n_isects), self.capacity, ptr(self.means2d), ptr(self.conics), ptr(self.colors),
             ptr(self.opacities), ptr(self.betas), ptr(backgrounds), None, 3, self.W, self.H, self.tile_size,
             ptr(self.offsets), ptr(self.flatten_ids), ptr(self.render_alphas), ptr(self.last_ids), ptr(v_rc),
@@ -177,11 +229,68 @@ class FusedRasterizer:
             ptr(self.v_betas), s), "ubs_rasterize_bwd")
         if v_records is None:
             v_records = torch.empty_like(records)
-        check(lib.ubs_fused_project_bwd(
+        with self._stage("fused_project_bwd"):
+          check(lib.ubs_fused_project_bwd(
             C, N, D, ptr(records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), self.W, self.H, self.eps2d,
             1 if self.aa else 0, ptr(self.radii), ptr(self.conics), ptr(self.v_means2d), None, ptr(self.v_conics),
             ptr(self.v_opacities), ptr(self.v_betas), ptr(self.v_colors), ptr(v_records), s), "ubs_fused_project_bwd")
         return v_records
+
+
+class HostPipeline:
+    """Host-buffer front end of the renderer: camera parameters come from pinned host memory, the finished image
+    goes back to pinned host memory, and `depth` frames are kept in flight so the device->host copy of frame k
+    overlaps the kernels of frame k+1 (separate copy stream, double-buffered device and host images).
+
+    Camera row layout (29 floats): viewmat 4x4 row-major | K 3x3 | camera centre xyz | timestamp."""
+
+    CAM_FLOATS = 29
+
+    def __init__(self, rz: "FusedRasterizer", depth: int = 2):
+        self.rz, self.depth = rz, depth
+        dev, C, H, W = rz.device, rz.C, rz.H, rz.W
+        assert C == 1, "HostPipeline renders one camera per frame"
+        self.cam_dev = [torch.empty((self.CAM_FLOATS,), dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.img_dev = [(torch.empty((C, H, W, 3), dtype=torch.float32, device=dev),
+                         torch.empty((C, H, W, 1), dtype=torch.float32, device=dev)) for _ in range(depth)]
+        self.img_host = [(torch.empty((C, H, W, 3), dtype=torch.float32).pin_memory(),
+                          torch.empty((C, H, W, 1), dtype=torch.float32).pin_memory()) for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copied = [None] * depth  # event: D2H of slot finished
+        self.k = 0
+
+    def render_to_host(self, records: Tensor, cam_row_pinned: Tensor, backgrounds: Optional[Tensor] = None):
+        """Queues one frame; returns the slot index whose host image will hold it after drain()/wait(slot)."""
+        slot = self.k % self.depth
+        self.k += 1
+        main = torch.cuda.current_stream()
+        if self.copied[slot] is not None:
+            main.wait_event(self.copied[slot])  # the slot's device image is free again
+        cam = self.cam_dev[slot]
+        cam.copy_(cam_row_pinned, non_blocking=True)
+        ts = cam[28:29] if self.rz.D == 7 else None
+        rc, ra = self.rz.forward(records, cam[0:16].view(1, 4, 4), cam[16:25].view(1, 3, 3), cam[25:28].view(1, 3), ts,
+                                 backgrounds, out=self.img_dev[slot])
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(done)
+            self.img_host[slot][0].copy_(rc, non_blocking=True)
+            self.img_host[slot][1].copy_(ra, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.copied[slot] = ev
+        return slot
+
+    def wait(self, slot: int):
+        if self.copied[slot] is not None:
+            self.copied[slot].synchronize()
+        return self.img_host[slot]
+
+    def drain(self):
+        for ev in self.copied:
+            if ev is not None:
+                ev.synchronize()
 
 
 class _FusedRender(torch.autograd.Function):
