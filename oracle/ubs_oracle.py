@@ -121,19 +121,23 @@ def _inv3x3_adjugate(a):
     return inv.reshape(-1, 3, 3)
 
 
-def cond_mean_convariance_opacity(means, covars, opacities, betas, query):
-    """Conditioning with the CUDA kernel's guards (cond_mean_convariance_opacity_fwd.cu:135-289).
-    means [N,D], covars [N,D,D], opacities [N,1], betas/query [N,Cd] -> [N,3], [N,3,3], [N,1]."""
+def _guard(den):
+    return torch.where(den == 0, torch.full_like(den, 1e-20), den)
+
+
+def _cond_parts(means, covars, opacities, betas, query):
+    """Forward of K3 with every intermediate the hand-written backward needs
+    (cond_mean_convariance_opacity_fwd.cu:135-289)."""
     N, D = means.shape
     Cd = D - 3
-    query = query.detach()  # no gradient to the query (cuda/_wrapper.py:611)
     v11, v12 = covars[:, :3, :3], covars[:, :3, 3:]
     v21, v22 = covars[:, 3:, :3], covars[:, 3:, 3:]
     x = query - means[:, 3:]
     beta_adj = torch.clamp_max(betas * 0.25, 1.0)
     # Gauss-Jordan with partial pivoting for Cd != 3 (fwd.cu:26-75) == LU-based inverse up to rounding
     vinv = _inv3x3_adjugate(v22) if Cd == 3 else torch.linalg.inv(v22)
-    rb = (v12 @ vinv) * beta_adj[:, None, :]
+    r_ = v12 @ vinv
+    rb = r_ * beta_adj[:, None, :]
     m_cond = means[:, :3] + (rb @ x[:, :, None])[:, :, 0]
     v_cond = v11 - rb @ v21
     # Cholesky of v22 reading its lower triangle, with the kernel's guards (fwd.cu:250-268)
@@ -144,26 +148,115 @@ def cond_mean_convariance_opacity(means, covars, opacities, betas, query):
             for k in range(j):
                 s = s - Lc[i][k] * Lc[j][k]
             if i == j:
-                s = torch.where(s <= 0, torch.full_like(s, 1e-20), s)
-                Lc[i][j] = torch.sqrt(s)
+                Lc[i][j] = torch.sqrt(torch.where(s <= 0, torch.full_like(s, 1e-20), s))
             else:
-                den = Lc[j][j]
-                den = torch.where(den == 0, torch.full_like(den, 1e-20), den)
-                Lc[i][j] = s / den
+                Lc[i][j] = s / _guard(Lc[j][j])
     y = []
     for i in range(Cd):  # forward solve Lc y = x (fwd.cu:270-279)
         s = x[:, i]
         for k in range(i):
             s = s - Lc[i][k] * y[k]
-        den = Lc[i][i]
-        den = torch.where(den == 0, torch.full_like(den, 1e-20), den)
-        y.append(s / den)
-    eps = torch.finfo(torch.float32).eps
+        y.append(s / _guard(Lc[i][i]))
+    upper = 1.0 - torch.finfo(torch.float32).eps
+    d = [torch.clamp(torch.tanh(y[i] * y[i]), 0.0, upper) for i in range(Cd)]
     o_change = torch.ones_like(y[0])
     for i in range(Cd):
-        d = torch.clamp(torch.tanh(y[i] * y[i]), 0.0, 1.0 - eps)
-        o_change = o_change * torch.pow(1.0 - d, betas[:, i])
-    return m_cond, v_cond, opacities * o_change[:, None]
+        o_change = o_change * torch.pow(1.0 - d[i], betas[:, i])
+    return dict(x=x, beta_adj=beta_adj, vinv=vinv, r_=r_, rb=rb, v12=v12, v21=v21, Lc=Lc, y=y, d=d,
+                o_change=o_change, m_cond=m_cond, v_cond=v_cond, upper=upper)
+
+
+class _Conditioning(torch.autograd.Function):
+    """K3 forward + the reference's HAND-WRITTEN backward K4 (cond_mean_convariance_opacity_bwd.cu:101-563).
+
+    The backward is restated line by line rather than left to autograd because the reference is not the exact
+    derivative of its forward: in the Cholesky backward it forms G = U L^-1 by solving with L where L^T is needed
+    (bwd.cu:495-510), so the opacity-path contribution to gV22 differs from autograd by several percent whenever L
+    is not diagonal.  Parity is defined against the reference, so the oracle (and the CUDA library) reproduce it."""
+
+    @staticmethod
+    def forward(ctx, means, covars, opacities, betas, query):
+        p = _cond_parts(means, covars, opacities, betas, query)
+        ctx.save_for_backward(means, covars, opacities, betas, query)
+        return p["m_cond"], p["v_cond"], opacities * p["o_change"][:, None]
+
+    @staticmethod
+    def backward(ctx, gM, gV, gO):
+        means, covars, opacities, betas, query = ctx.saved_tensors
+        p = _cond_parts(means, covars, opacities, betas, query)
+        N, D = means.shape
+        Cd = D - 3
+        x, beta_adj, i22, r_, rb, v12, v21 = p["x"], p["beta_adj"], p["vinv"], p["r_"], p["rb"], p["v12"], p["v21"]
+        Lc, y, d, o_change, upper = p["Lc"], p["y"], p["d"], p["o_change"], p["upper"]
+        gm = torch.zeros_like(means)
+        gVfull = torch.zeros_like(covars)
+        gm[:, :3] = gM  # bwd.cu:235
+        Gr = gM[:, :, None] * x[:, None, :] - gV @ v21.transpose(1, 2)  # bwd.cu:238-266
+        gx = torch.einsum("nrc,nr->nc", rb, gM)  # bwd.cu:247-253
+        gVfull[:, :3, :3] = gV  # bwd.cu:257-259
+        gVfull[:, 3:, :3] = -(rb.transpose(1, 2) @ gV)  # bwd.cu:269-275
+        dL_dba = (Gr * r_).sum(dim=1)  # bwd.cu:279-285
+        G_r = Gr * beta_adj[:, None, :]
+        gVfull[:, :3, 3:] = G_r @ i22.transpose(1, 2)  # bwd.cu:296-304
+        Gi22 = v12.transpose(1, 2) @ G_r  # bwd.cu:307-316
+        # ---- opacity path (bwd.cu:318-527)
+        opa, gOs = opacities[:, 0], gO[:, 0]
+        go = (gOs * o_change)[:, None]
+        g_o_change = gOs * opa
+        gb = torch.zeros_like(betas)
+        g_y = []
+        for i in range(Cd):
+            base = 1.0 - d[i]
+            pos = base > 0
+            safe = torch.where(pos, base, torch.ones_like(base))
+            gb[:, i] = torch.where(pos, g_o_change * o_change * torch.log(safe), torch.zeros_like(base))
+            active = pos & (d[i] > 0) & (d[i] < upper)
+            g_d = torch.where(active, g_o_change * (-o_change * betas[:, i] / safe), torch.zeros_like(base))
+            g_y.append(g_d * (2.0 * y[i] * (1.0 - d[i] * d[i])))
+        a = [None] * Cd
+        for i in range(Cd - 1, -1, -1):  # (L^T) a = g_y, bwd.cu:414-421
+            s = g_y[i]
+            for k in range(i + 1, Cd):
+                s = s - Lc[k][i] * a[k]
+            a[i] = s / _guard(Lc[i][i])
+        gx = gx + torch.stack(a, dim=1)
+        zero = torch.zeros_like(y[0])
+        L = [[Lc[r][c] if c <= r else zero for c in range(Cd)] for r in range(Cd)]
+        gL = [[-(a[r] * y[c]) if c <= r else zero for c in range(Cd)] for r in range(Cd)]
+        S = [[zero for _ in range(Cd)] for _ in range(Cd)]
+        for r in range(Cd):  # S = tril(L^T gL), diag * 0.5 (bwd.cu:458-481)
+            for c in range(r + 1):
+                acc = zero
+                for k in range(Cd):
+                    acc = acc + L[k][r] * gL[k][c]
+                S[r][c] = acc * 0.5 if r == c else acc
+        U = [[zero for _ in range(Cd)] for _ in range(Cd)]
+        for col in range(Cd):  # (L^T) U = S, bwd.cu:486-503
+            for i in range(Cd - 1, -1, -1):
+                s = S[i][col]
+                for k in range(i + 1, Cd):
+                    s = s - L[k][i] * U[k][col]
+                U[i][col] = s / _guard(L[i][i])
+        Gm = [[zero for _ in range(Cd)] for _ in range(Cd)]
+        for col in range(Cd):  # the reference's "G = U L^-1" (solved with L, as written: bwd.cu:505-524)
+            for i in range(Cd):
+                s = U[col][i]
+                for k in range(i):
+                    s = s - L[i][k] * Gm[k][col]
+                Gm[i][col] = s / _guard(L[i][i])
+        for r in range(Cd):
+            for c in range(Cd):
+                gVfull[:, 3 + r, 3 + c] += 0.5 * (Gm[r][c] + Gm[c][r])  # bwd.cu:527-533
+        gm[:, 3:] = -gx  # bwd.cu:538-539
+        gb = gb + dL_dba * torch.where(betas < 4.0, torch.full_like(betas, 0.25), torch.zeros_like(betas))
+        gVfull[:, 3:, 3:] += -(i22.transpose(1, 2) @ (Gi22 @ i22.transpose(1, 2)))  # bwd.cu:548-562
+        return gm, gVfull, go, gb, None
+
+
+def cond_mean_convariance_opacity(means, covars, opacities, betas, query):
+    """K3/K4 (cuda/_wrapper.py:18-31,573-611).  means [N,D], covars [N,D,D], opacities [N,1], betas/query [N,Cd]
+    -> [N,3], [N,3,3], [N,1].  No gradient to `query` (cuda/_wrapper.py:611)."""
+    return _Conditioning.apply(means, covars, opacities, betas, query.detach())
 
 
 def fully_fused_projection(means, covars6, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01, far_plane=1e10,
