@@ -122,3 +122,31 @@ def test_gradient_allreduce_two_ranks_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_gsplat_import_shim_resolves_reference_imports():
+    """The exact import statements of scene/beta_model.py:12-22 against the shim package."""
+    from gsplat.cuda._torch_impl import (  # noqa: F401
+        _cond_mean_convariance_opacity,
+        _l_triangle_to_rotmat,
+        _rot_scale_l_triangle_to_covar,
+    )
+    from gsplat.cuda._wrapper import (  # noqa: F401
+        cond_mean_convariance_opacity,
+        l_triangle_to_rotmat,
+        rot_scale_l_triangle_to_covar,
+    )
+    from gsplat.rendering import rasterization
+
+    import inspect
+
+    import ubs_b200
+
+    assert rasterization is ubs_b200.rasterization
+    params = list(inspect.signature(rasterization).parameters)
+    assert params == ["means", "l_triagnles", "scales", "opacities", "betas", "colors", "viewmats", "Ks", "width",
+                      "height", "near_plane", "far_plane", "radius_clip", "eps2d", "tile_size", "backgrounds",
+                      "render_mode", "rasterize_mode", "channel_chunk", "covars"]  # rendering.py:17-40
+    d = {k: v.default for k, v in inspect.signature(rasterization).parameters.items()}
+    assert (d["near_plane"], d["far_plane"], d["radius_clip"], d["eps2d"], d["tile_size"], d["render_mode"],
+            d["rasterize_mode"], d["channel_chunk"]) == (0.01, 1e10, 0.0, 0.3, 16, "RGB", "classic", 32)

@@ -272,7 +272,7 @@ extern "C" int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int6
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "rasterize_bwd: bad sizes");
     UBS_CHECK_ARG(tile_size == kTile, "rasterize_bwd: tile_size must be %d (got %d)", kTile, tile_size);
-    if (C == 0 || N == 0) return UBS_OK;
+    if (C == 0 || N == 0 || isect_capacity == 0) return UBS_OK;  // no pairs: every gradient stays zero
     UBS_CHECK_ARG(n_isects && offsets && means2d && conics && colors && opacities && betas && flatten_ids &&
                       render_alphas && last_ids && v_render_colors && v_render_alphas && v_means2d && v_conics &&
                       v_colors && v_opacities && v_betas,

@@ -251,7 +251,7 @@ extern "C" int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, int6
     UBS_CHECK_ARG(tile_size == kTile, "rasterize_fwd: tile_size must be %d (got %d)", kTile, tile_size);
     if (C == 0) return UBS_OK;
     UBS_CHECK_ARG(n_isects && offsets && render_colors && render_alphas && last_ids, "rasterize_fwd: null pointer");
-    UBS_CHECK_ARG(N == 0 || (means2d && conics && colors && opacities && betas && flatten_ids),
+    UBS_CHECK_ARG(N == 0 || (means2d && conics && colors && opacities && betas && (flatten_ids || isect_capacity == 0)),
                   "rasterize_fwd: null primitive arrays");
     UBS_CHECK_ARG(C <= 65535, "rasterize_fwd: C=%d exceeds 65535", C);
     cudaStream_t s = (cudaStream_t)stream;
