@@ -30,7 +30,7 @@ extern "C" {
 #define UBS_ENOSPC (-3)   /* caller-provided capacity / workspace too small            */
 #define UBS_EUNSUPPORTED (-4)
 
-#define UBS_MAX_CHANNELS 32 /* colour channels handled by one compositing launch      */
+#define UBS_MAX_CHANNELS 16 /* colour channels handled by one compositing launch      */
 
 /* ---- library ------------------------------------------------------------------------------------------ */
 const char *ubs_last_error(void);

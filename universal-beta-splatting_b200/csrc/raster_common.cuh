@@ -23,6 +23,30 @@ __device__ __forceinline__ SubTile sub_tile_of(uint32_t thread_rank) {
     return s;
 }
 
+// Shared-memory loads through an explicit 32-bit shared-window address: the address is formed once outside the
+// hot loop (the compiler otherwise re-derives the shared base from SR_CgaCtaId inside it).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));  // opaque to the optimiser: keeps the address in a register (no rematerialisation)
+    return a;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// MUFU.RCP without the range fix-up code that `1.f / x` expands to even under --use_fast_math
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 // Axis-aligned bounding box of the support {sigma < 1} of a 2-D Beta primitive with conic (a, b, c):
 // half extents sqrt(c / det), sqrt(a / det) with det = ac - b^2, inflated so that rounding can never cull a
 // pixel the exact test would accept.  Degenerate conics get an unbounded box (never culled).

@@ -98,7 +98,7 @@ rasterize_bwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         if (sigma < 0.f || sigma >= 1.f) return false;
         const float vis = __powf(1.f - sigma, beta);
         const float alpha = fminf(0.999f, opac * vis);
-        const float ra = 1.f / (1.f - alpha);
+        const float ra = fast_rcp(1.f - alpha);
         T *= ra;
         const float fac = alpha * T;
         float v_alpha = 0.f;
@@ -241,6 +241,227 @@ rasterize_bwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
     }
 }
 
+
+// ---- RGB fast path ---------------------------------------------------------------------------------------------
+// Same results as the generic kernel above for CH == 3, restructured for issue-slot count (the kernel is issue
+// bound):  * array-of-structs staging, 16-bit byte offsets in the per-warp lists, explicit shared addresses;
+//          * branch-free evaluation of a triple of pairs (invalid lanes contribute exact zeros), so the three
+//            evaluations interleave and only the triple-level "anything valid?" test branches;
+//          * the colour buffer of the reference (buffer[k], rasterize_to_pixels_bwd.cu:196-214) collapses to the
+//            scalar B = sum_k buffer[k] v_rc[k], and the term T_final (v_ra - bg.v_rc) is hoisted per pixel;
+//          * v_xy is linear in the moments Sx = sum v_sigma dx, Sy = sum v_sigma dy, so those are what the warp
+//            reduces; the conic products, the factor 2 and ln 2 are applied once per (tile, pair) at flush time.
+struct __align__(16) Staged3 {
+    float4 xyob;   // mean2d.x, mean2d.y, opacity, beta
+    float4 conic;  // a, 2b, c, (unused)
+    float4 col;    // r, g, b, (unused)
+};
+constexpr int kAccStride = 11;  // 10 accumulators per pair, odd stride -> conflict-free flush
+
+__global__ void __launch_bounds__(kTilePixels)
+rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev, int64_t isect_capacity,
+                      const float2 *__restrict__ means2d, const float *__restrict__ conics,
+                      const float *__restrict__ colors, const float *__restrict__ opacities,
+                      const float *__restrict__ betas, const float *__restrict__ backgrounds,
+                      const uint8_t *__restrict__ masks, uint32_t width, uint32_t height, uint32_t tile_width,
+                      uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
+                      const int32_t *__restrict__ flatten_ids, const float *__restrict__ render_alphas,
+                      const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
+                      const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
+                      float *__restrict__ v_conics, float *__restrict__ v_colors, float *__restrict__ v_opacities,
+                      float *__restrict__ v_betas) {
+    constexpr int kRec = (int)sizeof(Staged3);  // 48
+    const uint32_t cam = blockIdx.z;
+    const uint32_t tile_id = blockIdx.y * tile_width + blockIdx.x;
+    const uint32_t tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
+    const SubTile st = sub_tile_of(tr);
+    const uint32_t i = blockIdx.y * kTile + st.py;
+    const uint32_t j = blockIdx.x * kTile + st.px;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const bool inside = (i < height && j < width);
+
+    tile_offsets += (size_t)cam * tile_height * tile_width;
+    if (backgrounds != nullptr) backgrounds += cam * 3;
+    if (masks != nullptr && !masks[(size_t)cam * tile_height * tile_width + tile_id]) return;
+
+    const int64_t n_isects = min(*n_isects_dev, isect_capacity);
+    const int32_t range_start = tile_offsets[tile_id];
+    const int32_t range_end = (cam == (uint32_t)C - 1 && tile_id == tile_width * tile_height - 1)
+                                  ? (int32_t)n_isects
+                                  : tile_offsets[tile_id + 1];
+    const int32_t num_batches = (range_end - range_start + kTilePixels - 1) / kTilePixels;
+    if (num_batches <= 0) return;
+
+    __shared__ Staged3 s_rec[kTilePixels + 1];  // [kTilePixels] = sentinel (sigma = NaN) padding the lists
+    __shared__ float4 s_bbox[kTilePixels];
+    __shared__ int32_t s_id[kTilePixels];
+    __shared__ float s_acc[kTilePixels * kAccStride];
+    __shared__ __align__(8) uint16_t s_list[kTilePixels / 32][kTilePixels + 4];
+
+    const float wx0 = (float)(blockIdx.x * kTile + st.bx * kSubW) + 0.5f, wx1 = wx0 + (float)(kSubW - 1);
+    const float wy0 = (float)(blockIdx.y * kTile + st.by * kSubH) + 0.5f, wy1 = wy0 + (float)(kSubH - 1);
+    uint16_t *my_list = s_list[warp];
+    const uint32_t rec_addr = smem_addr(s_rec), list_addr = smem_addr(my_list);
+    const float kNaN = __int_as_float(0x7fffffff);
+    if (tr == 0) {
+        s_rec[kTilePixels].xyob = make_float4(kNaN, kNaN, 0.f, 1.f);
+        s_rec[kTilePixels].conic = make_float4(1.f, 0.f, 1.f, 0.f);
+        s_rec[kTilePixels].col = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // per-pixel state
+    const size_t pix = inside ? ((size_t)cam * height + i) * width + j : 0;
+    const float T_final = inside ? 1.f - render_alphas[pix] : 1.f;
+    float T = T_final;
+    const float v_r = inside ? v_render_colors[pix * 3 + 0] : 0.f;
+    const float v_g = inside ? v_render_colors[pix * 3 + 1] : 0.f;
+    const float v_b = inside ? v_render_colors[pix * 3 + 2] : 0.f;
+    float Kc = inside ? v_render_alphas[pix] : 0.f;  // becomes T_final (v_ra - bg . v_rc)
+    if (backgrounds != nullptr) Kc -= backgrounds[0] * v_r + backgrounds[1] * v_g + backgrounds[2] * v_b;
+    Kc *= T_final;
+    float B = 0.f;  // sum_k buffer[k] v_rc[k]
+    const int32_t bin_final = inside ? last_ids[pix] : -1;
+    int32_t warp_bin_final = bin_final;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+        warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, off));
+
+    for (int k = tr; k < kTilePixels * kAccStride; k += kTilePixels) s_acc[k] = 0.f;
+
+    // one (pixel, pair) evaluation; g[0..9] = rgb, (dx^2, dx dy, dy^2) v_sigma, Sx, Sy, v_opacity, v_beta / ln2.
+    // Branch-free: an invalid lane sees vis = 0 -> alpha = 0, ra = 1, every output an exact zero.
+    auto eval = [&](uint32_t off, uint32_t off_min, float *g) -> bool {
+        const uint32_t rec = rec_addr + off;
+        const float4 xyob = lds_f4(rec);
+        const float4 conic = lds_f4(rec + 16);
+        const float4 col = lds_f4(rec + 32);
+        const float dx = xyob.x - px, dy = xyob.y - py;
+        const float sigma = __fmaf_rn(dy, dx * conic.y, __fmaf_rn(dx, conic.x * dx, dy * (conic.z * dy)));
+        // pairs behind this pixel's last contributor (rasterize_to_pixels_bwd.cu:166-168) and sigma outside [0,1)
+        const bool valid = (__float_as_uint(sigma) < 0x3f800000u) && (off >= off_min);
+        const float om = 1.f - (valid ? sigma : 0.f);
+        const float lg = __log2f(om);
+        const float vis = valid ? exp2f(xyob.w * lg) : 0.f;
+        const float ov = xyob.z * vis;
+        const float alpha = fminf(0.999f, ov);
+        const float ra = fast_rcp(1.f - alpha);
+        T *= ra;
+        const float fac = alpha * T;
+        g[0] = fac * v_r;
+        g[1] = fac * v_g;
+        g[2] = fac * v_b;
+        const float cv = __fmaf_rn(col.z, v_b, __fmaf_rn(col.y, v_g, col.x * v_r));
+        const float v_alpha = __fmaf_rn(T, cv, ra * (Kc - B));
+        B = __fmaf_rn(fac, cv, B);
+        const bool live = ov <= 0.999f;  // the clamp has zero slope above it (rasterize_to_pixels_bwd.cu:230)
+        const float ov_g = live ? ov : 0.f;
+        const float vis_g = live ? vis : 0.f;
+        const float v_sigma = -(v_alpha * xyob.w) * (ov_g * fast_rcp(om));  // o beta (1-sigma)^(beta-1) = beta ov / (1-sigma)
+        const float tx = dx * v_sigma, ty = dy * v_sigma;
+        g[3] = tx * dx;
+        g[4] = tx * dy;
+        g[5] = ty * dy;
+        g[6] = tx;
+        g[7] = ty;
+        g[8] = vis_g * v_alpha;
+        g[9] = (v_alpha * ov_g) * lg;
+        return valid;
+    };
+
+    for (int32_t b = 0; b < num_batches; ++b) {
+        __syncthreads();  // previous batch fully consumed and flushed
+        const int32_t batch_end = range_end - 1 - kTilePixels * b;  // pair index held by slot 0 (furthest back)
+        const int32_t batch_size = min((int32_t)kTilePixels, batch_end + 1 - range_start);
+        const int32_t idx = batch_end - (int32_t)tr;
+        if (idx >= range_start) {
+            const int32_t g = flatten_ids[idx];
+            s_id[tr] = g;
+            const float2 xy = means2d[g];
+            const float ca = conics[(size_t)g * 3], cb = conics[(size_t)g * 3 + 1], cc = conics[(size_t)g * 3 + 2];
+            s_rec[tr].xyob = make_float4(xy.x, xy.y, opacities[g], betas[g]);
+            s_rec[tr].conic = make_float4(ca, cb + cb, cc, 0.f);
+            s_rec[tr].col = make_float4(colors[(size_t)g * 3], colors[(size_t)g * 3 + 1], colors[(size_t)g * 3 + 2], 0.f);
+            s_bbox[tr] = support_bbox(xy.x, xy.y, ca, cb, cc);
+        }
+        __syncthreads();
+
+        // slot p holds pair batch_end - p; a pixel takes part iff batch_end - p <= bin_final
+        const int32_t t_begin = max(0, batch_end - warp_bin_final);
+        const int64_t pmin = inside ? max((int64_t)0, (int64_t)batch_end - bin_final) : (int64_t)kTilePixels + 1;
+        const uint32_t off_min = (uint32_t)min(pmin, (int64_t)kTilePixels + 1) * kRec;
+        uint32_t cnt = 0;
+        for (int32_t p0 = t_begin & ~31; p0 < batch_size; p0 += 32) {
+            const int32_t p = p0 + (int32_t)lane;
+            bool hit = false;
+            if (p >= t_begin && p < batch_size) {
+                const float4 bb = s_bbox[p];
+                hit = (bb.x <= wx1) && (bb.y >= wx0) && (bb.z <= wy1) && (bb.w >= wy0);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (hit) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(p * kRec);
+            cnt += __popc(m);
+        }
+        if (lane < 3) my_list[cnt + lane] = (uint16_t)(kTilePixels * kRec);  // pad the last triple with the sentinel
+        __syncwarp();
+
+        for (uint32_t t = 0; t < cnt; t += 3) {
+            float v[32];
+            v[30] = 0.f, v[31] = 0.f;
+            const uint32_t o0 = lds_u16(list_addr + 2 * t), o1 = lds_u16(list_addr + 2 * t + 2),
+                           o2 = lds_u16(list_addr + 2 * t + 4);
+            bool any_valid = eval(o0, off_min, v);
+            any_valid |= eval(o1, off_min, v + kGrad3);
+            any_valid |= eval(o2, off_min, v + 2 * kGrad3);
+            if (!__any_sync(0xffffffffu, any_valid)) continue;
+            // transposing butterfly: afterwards v[0] of lane l is the warp-wide sum of component l
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool upper = (lane & off) != 0;
+#pragma unroll
+                for (int k = 0; k < off; ++k) {
+                    const float send = upper ? v[k] : v[k + off];
+                    const float keep = upper ? v[k + off] : v[k];
+                    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            const uint32_t q = lane / kGrad3, comp = lane - q * kGrad3;
+            const uint32_t oq = q == 0 ? o0 : (q == 1 ? o1 : o2);
+            if (lane < 3 * kGrad3 && oq < (uint32_t)(kTilePixels * kRec) && v[0] != 0.f)
+                atomicAdd(&s_acc[(oq / kRec) * kAccStride + comp], v[0]);
+        }
+        __syncthreads();
+
+        // flush: one set of global atomics per (tile, pair); finish the moment form here
+        if ((int32_t)tr < batch_size) {
+            float *acc = s_acc + tr * kAccStride;
+            float a[kGrad3];
+            bool nz = false;
+#pragma unroll
+            for (int k = 0; k < kGrad3; ++k) {
+                a[k] = acc[k];
+                nz |= (a[k] != 0.f);
+            }
+            if (nz) {
+                const size_t g = (size_t)s_id[tr];
+                const float4 conic = s_rec[tr].conic;  // a, 2b, c
+                atomicAdd(v_colors + g * 3 + 0, a[0]);
+                atomicAdd(v_colors + g * 3 + 1, a[1]);
+                atomicAdd(v_colors + g * 3 + 2, a[2]);
+                atomicAdd(v_conics + g * 3 + 0, a[3]);
+                atomicAdd(v_conics + g * 3 + 1, a[4] + a[4]);
+                atomicAdd(v_conics + g * 3 + 2, a[5]);
+                // v_xy = 2 v_sigma (a dx + b dy, b dx + c dy) summed over pixels = (2a Sx + 2b Sy, 2b Sx + 2c Sy)
+                atomicAdd(v_means2d + g * 2 + 0, __fmaf_rn(conic.x + conic.x, a[6], conic.y * a[7]));
+                atomicAdd(v_means2d + g * 2 + 1, __fmaf_rn(conic.y, a[6], (conic.z + conic.z) * a[7]));
+                atomicAdd(v_opacities + g, a[8]);
+                atomicAdd(v_betas + g, a[9] * 0.693147180559945f);  // lg2 -> ln
+#pragma unroll
+                for (int k = 0; k < kGrad3; ++k) acc[k] = 0.f;
+            }
+        }
+    }
+}
+
 template <int CH>
 int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const float *means2d, const float *conics,
                const float *colors, const float *opacities, const float *betas, const float *backgrounds,
@@ -250,10 +471,17 @@ int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
                float *v_betas, cudaStream_t s) {
     const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
     dim3 grid(tw, th, (unsigned)C), block(kTilePixels, 1, 1);
-    rasterize_bwd_kernel<CH><<<grid, block, 0, s>>>(
-        C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities, betas, backgrounds, masks,
-        (uint32_t)width, (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids, v_render_colors,
-        v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas);
+    if constexpr (CH == 3) {
+        rasterize_bwd3_kernel<<<grid, block, 0, s>>>(
+            C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities, betas, backgrounds, masks,
+            (uint32_t)width, (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids,
+            v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas);
+    } else {
+        rasterize_bwd_kernel<CH><<<grid, block, 0, s>>>(
+            C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities, betas, backgrounds, masks,
+            (uint32_t)width, (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids,
+            v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas);
+    }
     UBS_LAUNCH_CHECK("rasterize_bwd_kernel");
     return UBS_OK;
 }
@@ -290,9 +518,8 @@ extern "C" int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int6
         UBS_BWD_CASE(4)
         UBS_BWD_CASE(8)
         UBS_BWD_CASE(16)
-        UBS_BWD_CASE(32)
         default:
-            set_error("rasterize_bwd: unsupported channel count %d (supported: 1,2,3,4,8,16,32)", channels);
+            set_error("rasterize_bwd: unsupported channel count %d (supported: 1,2,3,4,8,16)", channels);
             return UBS_EUNSUPPORTED;
     }
 #undef UBS_BWD_CASE

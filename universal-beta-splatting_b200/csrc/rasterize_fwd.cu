@@ -22,6 +22,8 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
                      uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
                      const int32_t *__restrict__ flatten_ids, float *__restrict__ render_colors,
                      float *__restrict__ render_alphas, int32_t *__restrict__ last_ids) {
+    constexpr bool kPacked = CH <= 4;        // colour rides in one float4 of the staged record
+    constexpr int kColW = kPacked ? 4 : CH;  // floats of colour per staged pair
     const uint32_t cam = blockIdx.z;
     const uint32_t tile_id = blockIdx.y * tile_width + blockIdx.x;
     const uint32_t tr = threadIdx.x;
@@ -52,29 +54,45 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
     const int32_t n_pairs = range_end - range_start;
     const int32_t num_batches = (n_pairs + kTilePixels - 1) / kTilePixels;
 
-    __shared__ float4 s_xyob[kTilePixels];   // mean2d.x, mean2d.y, opacity, beta
-    __shared__ float4 s_conic[kTilePixels];  // conic a, b, c, (unused)
-    __shared__ float4 s_bbox[kTilePixels];   // xmin, xmax, ymin, ymax of the sigma < 1 ellipse (inflated)
-    __shared__ float s_color[kTilePixels * CH];
-    __shared__ uint8_t s_list[kTilePixels / 32][kTilePixels];  // per-warp compacted pair indices
+    // staged 2-D records of one 256-pair batch (array of structs: one address computation per pair in the hot loop)
+    struct __align__(16) Staged {
+        float4 xyob;   // mean2d.x, mean2d.y, opacity, beta
+        float4 conic;  // conic a, 2b, c, (unused)
+        float col[kColW];
+    };
+    constexpr int kUnroll = 4;
+    static_assert((kTilePixels + 1) * sizeof(Staged) <= 65535, "staged-record offsets must fit 16 bits");
+    __shared__ Staged s_rec[kTilePixels + 1];  // [kTilePixels] = sentinel whose sigma is NaN (pads the lists)
+    __shared__ float4 s_bbox[kTilePixels];     // xmin, xmax, ymin, ymax of the sigma < 1 ellipse (inflated)
+    // per-warp compacted lists of byte offsets into s_rec, padded to a multiple of kUnroll with the sentinel
+    __shared__ __align__(8) uint16_t s_list[kTilePixels / 32][kTilePixels + kUnroll];
 
     // pixel-centre rectangle of this warp's 8x4 sub-tile
     const float wx0 = (float)(blockIdx.x * kTile + st.bx * kSubW) + 0.5f, wx1 = wx0 + (float)(kSubW - 1);
     const float wy0 = (float)(blockIdx.y * kTile + st.by * kSubH) + 0.5f, wy1 = wy0 + (float)(kSubH - 1);
     const uint32_t lane = tr & 31, warp = tr >> 5;
+    uint16_t *my_list = s_list[warp];
+    const uint32_t rec_addr = smem_addr(s_rec), list_addr = smem_addr(my_list);
+    const float kNaN = __int_as_float(0x7fffffff);
+    if (tr == 0) {
+        s_rec[kTilePixels].xyob = make_float4(kNaN, kNaN, 0.f, 1.f);
+        s_rec[kTilePixels].conic = make_float4(1.f, 0.f, 1.f, 0.f);
+    }
 
-    float T = 1.f;
+    // "done" is carried in the sign of T: a finished pixel (or one outside the image) holds -T, so that
+    // next_T = T (1 - alpha) is negative, fails `next_T > 1e-4`, and the lane idles through the rest of the list
+    // without a separate predicate in the loop; |T| is the transmittance before the primitive that tripped it.
+    float T = inside ? 1.f : -1.f;
     int32_t cur_idx = 0;
-    bool done = !inside;
     float pix_out[CH];
 #pragma unroll
     for (int k = 0; k < CH; ++k) pix_out[k] = 0.f;
 
     // register double buffer: the record this thread will publish for the next batch
     float4 r_xyob = make_float4(0.f, 0.f, 0.f, 0.f), r_conic = r_xyob;
-    float r_color[CH];
+    float r_color[kColW];
 #pragma unroll
-    for (int k = 0; k < CH; ++k) r_color[k] = 0.f;
+    for (int k = 0; k < kColW; ++k) r_color[k] = 0.f;
     auto gather = [&](int32_t batch) {
         const int32_t idx = range_start + batch * kTilePixels + (int32_t)tr;
         if (idx < range_end) {
@@ -90,18 +108,22 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
 
     for (int32_t b = 0; b < num_batches; ++b) {
         // everyone has finished reading the previous batch; stop when every pixel of the tile is done
-        if (__syncthreads_count(done) >= kTilePixels) break;
-        s_xyob[tr] = r_xyob;
-        s_conic[tr] = r_conic;
+        if (__syncthreads_count(T < 0.f) >= kTilePixels) break;
+        s_rec[tr].xyob = r_xyob;
         s_bbox[tr] = support_bbox(r_xyob.x, r_xyob.y, r_conic.x, r_conic.y, r_conic.z);
+        s_rec[tr].conic = make_float4(r_conic.x, r_conic.y + r_conic.y, r_conic.z, 0.f);  // b + b as the reference forms it
+        if constexpr (kPacked) {
+            *reinterpret_cast<float4 *>(s_rec[tr].col) = make_float4(r_color[0], r_color[1], r_color[2], r_color[3]);
+        } else {
 #pragma unroll
-        for (int k = 0; k < CH; ++k) s_color[tr * CH + k] = r_color[k];
+            for (int k = 0; k < CH; ++k) s_rec[tr].col[k] = r_color[k];
+        }
         __syncthreads();
         if (b + 1 < num_batches) gather(b + 1);  // in flight while this batch is composited
 
         const int32_t batch_start = range_start + b * kTilePixels;
         const int32_t batch_size = min((int32_t)kTilePixels, range_end - batch_start);
-        if (__all_sync(0xffffffffu, done)) continue;  // whole warp finished: nothing to composite
+        if (__all_sync(0xffffffffu, T < 0.f)) continue;  // whole warp finished: nothing to composite
 
         // warp-level cull: keep (in order) only the pairs whose support touches this warp's 8x4 pixels
         uint32_t cnt = 0;
@@ -113,33 +135,53 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
                 hit = (bb.x <= wx1) && (bb.y >= wx0) && (bb.z <= wy1) && (bb.w >= wy0);
             }
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (hit) s_list[warp][cnt + __popc(m & ((1u << lane) - 1u))] = (uint8_t)p;
+            if (hit) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(p * (int32_t)sizeof(Staged));
             cnt += __popc(m);
         }
+        if (lane < kUnroll) my_list[cnt + lane] = (uint16_t)(kTilePixels * sizeof(Staged));
         __syncwarp();
 
-        for (uint32_t t = 0; t < cnt && !done; ++t) {
-            const uint32_t p = s_list[warp][t];
-            const float4 conic = s_conic[p];
-            const float4 xyob = s_xyob[p];
+        int32_t last_off = -1;
+        for (uint32_t t = 0; t < cnt; t += kUnroll) {
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t off = lds_u16(list_addr + 2 * (t + u));
+            const uint32_t rec = rec_addr + off;
+            const float4 xyob = lds_f4(rec);
+            const float4 conic = lds_f4(rec + 16);
             const float dx = xyob.x - px, dy = xyob.y - py;
-            const float sigma = (conic.x * dx * dx + conic.z * dy * dy) + 2.f * conic.y * dx * dy;
-            if (sigma < 0.f || sigma >= 1.f) continue;
+            // same association as the reference's compiled form (rasterize_to_pixels_fwd.cu:143-145):
+            // sigma = fma(dy, dx * (b + b), fma(dx, a * dx, dy * (c * dy)))
+            const float sigma = __fmaf_rn(dy, dx * conic.y, __fmaf_rn(dx, conic.x * dx, dy * (conic.z * dy)));
+            // sigma in [0, 1)  <=>  its bit pattern is below that of 1.0f (negatives and NaN compare above)
+            if (__float_as_uint(sigma) >= 0x3f800000u) continue;
             const float alpha = fminf(0.999f, xyob.z * __powf(1.f - sigma, xyob.w));
             const float next_T = T * (1.f - alpha);
-            if (next_T <= 1e-4f) {  // this pixel is done; the primitive is NOT accumulated
-                done = true;
-                break;
+            if (!(next_T > 1e-4f)) {  // this pixel is done (now or earlier); the primitive is NOT accumulated
+                T = __uint_as_float(__float_as_uint(T) | 0x80000000u);
+                continue;
             }
             const float vis = alpha * T;
+            if constexpr (kPacked) {
+                const float4 col = lds_f4(rec + 32);
+                pix_out[0] += col.x * vis;
+                if constexpr (CH > 1) pix_out[1] += col.y * vis;
+                if constexpr (CH > 2) pix_out[2] += col.z * vis;
+                if constexpr (CH > 3) pix_out[3] += col.w * vis;
+            } else {
 #pragma unroll
-            for (int k = 0; k < CH; ++k) pix_out[k] += s_color[p * CH + k] * vis;
-            cur_idx = batch_start + (int32_t)p;
+                for (int k = 0; k < CH; ++k)
+                    pix_out[k] += reinterpret_cast<const Staged *>(reinterpret_cast<const unsigned char *>(s_rec) + off)->col[k] * vis;
+            }
+            last_off = (int32_t)off;
             T = next_T;
+          }
         }
+        if (last_off >= 0) cur_idx = batch_start + last_off / (int32_t)sizeof(Staged);
     }
 
     if (inside) {
+        T = fabsf(T);
         render_alphas[pix] = 1.f - T;
 #pragma unroll
         for (int k = 0; k < CH; ++k)
@@ -147,7 +189,6 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         last_ids[pix] = cur_idx;
     }
 }
-
 
 // Diagnostic (not on the hot path): work counters for the roofline bookkeeping of SURVEY.md 8(d).
 //   counts[0] = E_test: (pixel, pair) evaluations the reference algorithm performs (every pair of the tile list
@@ -266,9 +307,8 @@ extern "C" int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, int6
         UBS_FWD_CASE(4)
         UBS_FWD_CASE(8)
         UBS_FWD_CASE(16)
-        UBS_FWD_CASE(32)
         default:
-            set_error("rasterize_fwd: unsupported channel count %d (supported: 1,2,3,4,8,16,32; pad on the host)",
+            set_error("rasterize_fwd: unsupported channel count %d (supported: 1,2,3,4,8,16; pad on the host)",
                       channels);
             return UBS_EUNSUPPORTED;
     }

@@ -13,7 +13,7 @@ from torch import Tensor
 from . import _lib
 from ._lib import check, ptr
 
-SUPPORTED_CHANNELS = (1, 2, 3, 4, 8, 16, 32)
+SUPPORTED_CHANNELS = (1, 2, 3, 4, 8, 16)  # one compositing launch; wider colour vectors are chunked
 
 
 def _stream():
@@ -314,8 +314,17 @@ def rasterize_to_pixels(
     if channels > 513 or channels == 0:
         raise ValueError(f"Unsupported number of color channels: {channels}")
     if channels > SUPPORTED_CHANNELS[-1]:
-        raise ValueError(f"ubs_b200 composites at most {SUPPORTED_CHANNELS[-1]} channels per call "
-                         f"(rasterization() chunks with channel_chunk=32); got {channels}")
+        # channels composite independently: split into launches of <= 16 (the reference instead instantiates its
+        # kernel for up to 513 channels, rasterize_to_pixels_fwd.cu:338-357); alphas are identical in every chunk
+        w = SUPPORTED_CHANNELS[-1]
+        outs, alphas = [], None
+        for c0 in range(0, channels, w):
+            rc, ra = rasterize_to_pixels(means2d, conics, colors[..., c0:c0 + w], opacities, betas, image_width,
+                                         image_height, tile_size, isect_offsets, flatten_ids,
+                                         backgrounds[..., c0:c0 + w] if backgrounds is not None else None, masks)
+            outs.append(rc)
+            alphas = ra if alphas is None else alphas
+        return torch.cat(outs, dim=-1), alphas
     padded_channels = 0
     if channels not in SUPPORTED_CHANNELS:
         padded_channels = min(c for c in SUPPORTED_CHANNELS if c >= channels) - channels
