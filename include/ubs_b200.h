@@ -138,6 +138,28 @@ int ubs_isect_emit_sort(int C, int64_t N, const float *means2d, const int32_t *r
 /* stand-alone offset encoding of already sorted keys (isect_tiles.cu:287-366). n_isects is a host value.     */
 int ubs_isect_offset_encode(int64_t n_isects, const int64_t *isect_ids, int C, int tile_width, int tile_height,
                             int32_t *offsets, void *stream);
+
+/* ---- K7-K9, B200-first route: tile binning + per-tile segment sort -------------------------------------- */
+/* Same outputs as ubs_isect_count + ubs_isect_emit_sort (tiles_per_gauss, *n_isects, isect_ids and flatten_ids in
+ * the reference's sorted order, offsets[C,th,tw]; reference: isect_tiles.cu:99-333) without a global sort: per-tile
+ * pair counts come from a 2-D prefix sum of rectangle corner deltas, their exclusive scan is `offsets`, pairs are
+ * written straight into their tile's segment and each segment is sorted in shared memory by (depth bits, flatten id)
+ * -- the total order the reference's stable sort produces, so the result is bit-exact (csrc/bin_sort.cu).
+ * Requires depths >= +0 for every primitive with radii > 0 (near_plane > 0); otherwise use ubs_isect_emit_sort.
+ *   deltas_ready = 1: ubs_fused_project_fwd(tile_delta = workspace) already accumulated the corner deltas
+ *   deltas_ready = 0: computed here from means2d / radii (tiles_per_gauss [C,N] is then written if non-NULL)
+ * capacity bounds the pair arrays exactly as in ubs_isect_emit_sort (*status bit 0 on overflow; offsets are then
+ * clamped to capacity).  No host synchronisation.                                                            */
+size_t ubs_isect_bin_workspace_bytes(int C, int tile_width, int tile_height, int64_t capacity);
+int ubs_isect_bin_sort(int C, int64_t N, const float *means2d, const int32_t *radii, const float *depths,
+                       int tile_size, int tile_width, int tile_height, int deltas_ready,
+                       int32_t *tiles_per_gauss, /* [C,N] out when deltas_ready == 0, may be NULL */
+                       int64_t capacity, int64_t *n_isects, /* [1] device, out */
+                       int64_t *isect_ids,                  /* [capacity] */
+                       int32_t *flatten_ids,                /* [capacity] */
+                       int32_t *offsets,                    /* [C,th,tw]  */
+                       int32_t *status,                     /* [1] device or NULL */
+                       void *workspace, size_t workspace_bytes, void *stream);
 /* stand-alone stable radix sort of (int64 key, int32 val) pairs on bits [begin_bit, end_bit); n on device.   */
 size_t ubs_radix_sort_workspace_bytes(int64_t capacity);
 int ubs_radix_sort_pairs(const int64_t *n_dev, int64_t capacity, int64_t *keys_in, int32_t *vals_in, int64_t *keys_out,
@@ -172,7 +194,8 @@ int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_c
                       void *stream);
 
 /* Diagnostic work counters for the compositing roofline (no reference counterpart):
- * counts[4] (device u64) = { E_test, E_acc, E_cull, pairs staged } -- see csrc/rasterize_fwd.cu.              */
+ * counts[8] (device u64) = { E_test, E_acc, E_cull, pairs staged, E_any, E_cull4, E_any4, E_any8x2 } -- see
+ * csrc/rasterize_fwd.cu.                                                                                    */
 int ubs_rasterize_count(int C, const int64_t *n_isects, int64_t isect_capacity, const float *means2d,
                         const float *conics, const float *opacities, const float *betas, int width, int height,
                         int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
@@ -191,6 +214,10 @@ int ubs_rasterize_count(int C, const int64_t *n_isects, int64_t isect_capacity, 
 #define UBS_RECORD_STRIDE(D) ((UBS_RECORD_FLOATS(D) + 3) / 4 * 4)
 int ubs_record_stride(int D);
 
+/* tile_delta: NULL, or the start of a ubs_isect_bin_sort workspace: the kernel then also adds every visible
+ * primitive's four tile-rectangle corner deltas to it (the grid is zeroed first) and the call to
+ * ubs_isect_bin_sort(..., deltas_ready = 1, ...) that follows produces *n_isects; with tile_delta == NULL the
+ * pair count is written to *n_isects here (block sums in `workspace`, for ubs_isect_emit_sort).             */
 int ubs_fused_project_fwd(int C, int64_t N, int D, const float *records, /* [N, stride] */
                           const float *viewmats,                         /* [C,4,4] */
                           const float *Ks,                               /* [C,3,3] */
@@ -207,8 +234,10 @@ int ubs_fused_project_fwd(int C, int64_t N, int D, const float *records, /* [N, 
                           float *betas,             /* [C,N] spatial beta = 4 exp(raw beta_0) */
                           float *colors,            /* [C,N,3] or NULL (rgb copied out of the record) */
                           int32_t *tiles_per_gauss, /* [C,N] */
-                          int64_t *n_isects,        /* [1] device */
-                          void *workspace, size_t workspace_bytes, /* ubs_isect_workspace_bytes(C*N, cap) */
+                          int32_t *tile_delta,      /* NULL or start of the bin-sort workspace (see above) */
+                          int64_t *n_isects,        /* [1] device (may be NULL when tile_delta is given) */
+                          void *workspace, size_t workspace_bytes, /* ubs_isect_workspace_bytes(C*N, cap); unused
+                                                                      when tile_delta is given */
                           void *stream);
 /* backward of the above: consumes gradients w.r.t. the screen-space records and writes a packed gradient
  * record buffer (same layout as `records`; accumulated over cameras; zeroed by callee).                      */

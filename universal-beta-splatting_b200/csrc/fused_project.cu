@@ -110,7 +110,8 @@ fused_project_fwd_kernel(int C, int64_t N, const float *__restrict__ records, co
                          int calc_comp, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
                          int32_t *__restrict__ radii, float *__restrict__ means2d, float *__restrict__ depths,
                          float *__restrict__ conics, float *__restrict__ opacities, float *__restrict__ betas,
-                         float *__restrict__ colors, int32_t *__restrict__ tiles_per_gauss) {
+                         float *__restrict__ colors, int32_t *__restrict__ tiles_per_gauss,
+                         int32_t *__restrict__ tile_delta) {
     constexpr int Cd = D - 3;
     constexpr int STRIDE = UBS_RECORD_STRIDE(D);
     __shared__ __align__(128) float s_rec[kFusedThreads * STRIDE];
@@ -176,6 +177,8 @@ fused_project_fwd_kernel(int C, int64_t N, const float *__restrict__ records, co
         if (o.radius > 0) {
             const TileRect t = tile_rect(o.mean2d[0], o.mean2d[1], o.radius, tile_size, tile_width, tile_height);
             cnt = (int32_t)((t.y1 - t.y0) * (t.x1 - t.x0));
+            if (tile_delta != nullptr && cnt > 0)
+                add_tile_deltas(tile_delta + (size_t)cid * ((tile_height + 1) * (tile_width + 1)), t, tile_width);
         }
         radii[idx] = o.radius;
         reinterpret_cast<float2 *>(means2d)[idx] = make_float2(o.mean2d[0], o.mean2d[1]);
@@ -405,25 +408,29 @@ extern "C" int ubs_fused_project_fwd(int C, int64_t N, int D, const float *recor
                                      float far_plane, float radius_clip, int calc_compensations, int tile_size,
                                      int tile_width, int tile_height, int32_t *radii, float *means2d, float *depths,
                                      float *conics, float *opacities, float *betas, float *colors,
-                                     int32_t *tiles_per_gauss, int64_t *n_isects, void *workspace,
-                                     size_t workspace_bytes, void *stream) {
+                                     int32_t *tiles_per_gauss, int32_t *tile_delta, int64_t *n_isects,
+                                     void *workspace, size_t workspace_bytes, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0 && tile_size > 0, "fused_project_fwd: bad sizes");
     UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_fwd: D must be 6 or 7 (got %d)", D);
-    UBS_CHECK_ARG(n_isects != nullptr, "fused_project_fwd: n_isects is null");
+    UBS_CHECK_ARG(n_isects != nullptr || tile_delta != nullptr, "fused_project_fwd: n_isects is null");
+    UBS_CHECK_ARG(tile_width > 0 && tile_height > 0, "fused_project_fwd: bad tile grid");
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t CN = (int64_t)C * N;
+    // tile binning route (ubs_isect_bin_sort with deltas_ready = 1): zero this frame's corner-delta grid
+    if (tile_delta != nullptr && C > 0)
+        UBS_CUDA_TRY(cudaMemsetAsync(tile_delta, 0, bin_delta_bytes(C, tile_width, tile_height), s));
     if (CN == 0) {
-        UBS_CUDA_TRY(cudaMemsetAsync(n_isects, 0, sizeof(int64_t), s));
+        if (n_isects != nullptr) UBS_CUDA_TRY(cudaMemsetAsync(n_isects, 0, sizeof(int64_t), s));
         return UBS_OK;
     }
     UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && means2d && depths && conics && opacities && betas &&
-                      tiles_per_gauss && workspace,
+                      tiles_per_gauss && (workspace || tile_delta),
                   "fused_project_fwd: null pointer");
     UBS_CHECK_ARG(D != 7 || timestamps != nullptr, "fused_project_fwd: D=7 needs timestamps");
     UBS_CHECK_ARG(((uintptr_t)records & 15) == 0, "fused_project_fwd: records must be 16-byte aligned");
     UBS_CHECK_ARG(CN < ((int64_t)1 << 31), "fused_project_fwd: C*N must fit int32 flatten ids");
-    if (workspace_bytes < ubs_isect_workspace_bytes(CN, 0)) {
+    if (tile_delta == nullptr && workspace_bytes < ubs_isect_workspace_bytes(CN, 0)) {
         set_error("fused_project_fwd: workspace %zu < %zu", workspace_bytes, ubs_isect_workspace_bytes(CN, 0));
         return UBS_ENOSPC;
     }
@@ -439,11 +446,12 @@ extern "C" int ubs_fused_project_fwd(int C, int64_t N, int D, const float *recor
     fused_project_fwd_kernel<DD><<<grid, kFusedThreads, 0, s>>>(                                                       \
         C, N, records, viewmats, Ks, cam_pos, timestamps, prim_mask, (uint32_t)width, (uint32_t)height, eps2d,         \
         near_plane, far_plane, radius_clip, calc_compensations, (uint32_t)tile_size, (uint32_t)tile_width,             \
-        (uint32_t)tile_height, radii, means2d, depths, conics, opacities, betas, colors, tiles_per_gauss)
+        (uint32_t)tile_height, radii, means2d, depths, conics, opacities, betas, colors, tiles_per_gauss, tile_delta)
     if (D == 6) UBS_FUSED_LAUNCH(6);
     else UBS_FUSED_LAUNCH(7);
 #undef UBS_FUSED_LAUNCH
     UBS_LAUNCH_CHECK("fused_project_fwd_kernel");
+    if (tile_delta != nullptr) return UBS_OK;  // the pair count comes out of ubs_isect_bin_sort's scan
     return isect_blocksums_from_counts(CN, tiles_per_gauss, workspace, n_isects, s);
 }
 

@@ -119,25 +119,28 @@ isect_offsets_kernel(const int64_t *__restrict__ n_dev, int64_t n_host, int64_t 
         if (status != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, 1);
         n = capacity;
     }
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n == 0) {
-        if (idx < n_slots) offsets[idx] = 0;
+        for (int64_t idx = first; idx < n_slots; idx += stride) offsets[idx] = 0;
         return;
     }
-    if (idx >= n) return;
-    const int64_t hi = isect_ids[idx] >> 32;
-    const int64_t slot = (hi >> tile_n_bits) * n_tiles + (hi & tile_mask);
-    if (idx == 0) {
-        for (int64_t i = 0; i <= slot; ++i) offsets[i] = 0;
-    } else {
-        const int64_t hp = isect_ids[idx - 1] >> 32;
-        if (hp != hi) {
-            const int64_t slot_prev = (hp >> tile_n_bits) * n_tiles + (hp & tile_mask);
-            for (int64_t i = slot_prev + 1; i <= slot; ++i) offsets[i] = (int32_t)idx;
+    // grid-stride over the n pairs actually present (the grid is bounded, not sized by the capacity)
+    for (int64_t idx = first; idx < n; idx += stride) {
+        const int64_t hi = isect_ids[idx] >> 32;
+        const int64_t slot = (hi >> tile_n_bits) * n_tiles + (hi & tile_mask);
+        if (idx == 0) {
+            for (int64_t i = 0; i <= slot; ++i) offsets[i] = 0;
+        } else {
+            const int64_t hp = isect_ids[idx - 1] >> 32;
+            if (hp != hi) {
+                const int64_t slot_prev = (hp >> tile_n_bits) * n_tiles + (hp & tile_mask);
+                for (int64_t i = slot_prev + 1; i <= slot; ++i) offsets[i] = (int32_t)idx;
+            }
         }
-    }
-    if (idx == n - 1) {
-        for (int64_t i = slot + 1; i < n_slots; ++i) offsets[i] = (int32_t)n;
+        if (idx == n - 1) {
+            for (int64_t i = slot + 1; i < n_slots; ++i) offsets[i] = (int32_t)n;
+        }
     }
 }
 
@@ -253,7 +256,11 @@ extern "C" int ubs_isect_emit_sort(int C, int64_t N, const float *means2d, const
     }
     if (offsets != nullptr && n_slots > 0) {
         const int64_t work = capacity > (int64_t)n_slots ? capacity : (int64_t)n_slots;
-        isect_offsets_kernel<<<(unsigned)ceil_div(work, 256), 256, 0, s>>>(n_isects, 0, capacity, isect_ids, n_slots,
+        int sm = ubs_device_sm_count();
+        if (sm <= 0) sm = 148;
+        const int64_t max_blocks = (int64_t)sm * 16;
+        const int64_t blocks = ceil_div(work, 256) < max_blocks ? ceil_div(work, 256) : max_blocks;
+        isect_offsets_kernel<<<(unsigned)blocks, 256, 0, s>>>(n_isects, 0, capacity, isect_ids, n_slots,
                                                                            n_tiles, (uint32_t)tile_n_bits, offsets,
                                                                            status);
         UBS_LAUNCH_CHECK("isect_offsets_kernel");

