@@ -32,20 +32,25 @@ constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kSegItems = 8;                       // elements per thread in the shared-memory sort
 constexpr int kSegMax = kSegThreads * kSegItems;   // longest segment sorted in shared memory
 constexpr int kScanThreads = 1024;
+// Atomic targets are spread to one per 32-byte sector: with 4-byte spacing the whole cursor array sits in a few
+// L2 slices and one slice's atomic unit saturates (lts__d_atomic_input_cycles_active: max 65 %, mean 8.5 %).
+constexpr int kCursorStride = 8;
 
 struct BinWorkspace {
     int32_t *delta;      // [C][(th+1)*(tw+1)] corner deltas (zeroed per frame)
-    int32_t *cursor;     // [C*n_tiles] next free slot of every tile segment
+    int32_t *cursor;     // [C*n_tiles*kCursorStride] next free slot of every tile segment
     int64_t *cam_total;  // [C] pairs per camera
     uint64_t *keyval;    // [capacity] depth_bits << 32 | flatten_id, grouped by tile
     uint64_t *alt;       // [capacity] ping-pong buffer of the long-segment sort
 };
 
-size_t delta_bytes(int C, int tw, int th) { return align_up(sizeof(int32_t) * (size_t)C * (th + 1) * (tw + 1), 256); }
+size_t delta_bytes(int C, int tw, int th) {
+    return align_up(sizeof(int32_t) * (size_t)C * (th + 1) * (tw + 1) * kDeltaStride, 256);
+}
 
 size_t bin_ws_bytes(int C, int tw, int th, int64_t capacity) {
     size_t b = delta_bytes(C, tw, th);
-    b += align_up(sizeof(int32_t) * (size_t)C * tw * th, 256);
+    b += align_up(sizeof(int32_t) * (size_t)C * tw * th * kCursorStride, 256);
     b += align_up(sizeof(int64_t) * (size_t)(C > 0 ? C : 1), 256);
     b += 2 * align_up(sizeof(uint64_t) * (size_t)capacity, 256);
     return b;
@@ -57,7 +62,7 @@ BinWorkspace bin_carve(void *base, int C, int tw, int th, int64_t capacity) {
     w.delta = (int32_t *)p;
     p += delta_bytes(C, tw, th);
     w.cursor = (int32_t *)p;
-    p += align_up(sizeof(int32_t) * (size_t)C * tw * th, 256);
+    p += align_up(sizeof(int32_t) * (size_t)C * tw * th * kCursorStride, 256);
     w.cam_total = (int64_t *)p;
     p += align_up(sizeof(int64_t) * (size_t)(C > 0 ? C : 1), 256);
     w.keyval = (uint64_t *)p;
@@ -79,7 +84,8 @@ bin_count_kernel(int64_t CN, int64_t N, const float *__restrict__ means2d, const
         const float2 m = reinterpret_cast<const float2 *>(means2d)[idx];
         const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_width, tile_height);
         cnt = (int32_t)((t.y1 - t.y0) * (t.x1 - t.x0));
-        if (cnt > 0) add_tile_deltas(delta + (idx / N) * (int64_t)((tile_height + 1) * (tile_width + 1)), t, tile_width);
+        if (cnt > 0) add_tile_deltas(delta + (idx / N) * (int64_t)((tile_height + 1) * (tile_width + 1)) * kDeltaStride, t,
+                                     tile_width);
     }
     if (tiles_per_gauss != nullptr) tiles_per_gauss[idx] = cnt;
 }
@@ -109,24 +115,25 @@ __device__ __forceinline__ int64_t block_inclusive_scan_i64(int64_t v, int64_t *
     return base + incl;
 }
 
-// Phase 1 (one CTA per camera): delta grid -> per-tile counts (written into `offsets`), camera total.
-__device__ void bin_counts_of_camera(int32_t *delta, uint32_t tw, uint32_t th, int32_t *counts, int64_t *cam_total,
-                                     int64_t *s_warp) {
-    const uint32_t gw = tw + 1;
+// Phase 1 (one CTA per camera): delta grid -> per-tile counts (written to `counts`), camera total.  `g` is the
+// grid the 2-D prefix sum runs in: a compact copy in shared memory when it fits (every dependent step is then a
+// 29-cycle shared access instead of an L2 round trip), else the strided global delta grid itself.
+__device__ void bin_counts_of_camera(int32_t *g, uint32_t gw, uint32_t gs, uint32_t tw, uint32_t th, int32_t *counts,
+                                     int64_t *cam_total, int64_t *s_warp) {
     // rows: inclusive scan along x, one warp per row
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t y = warp; y < th; y += kScanThreads / 32) {
         int32_t carry = 0;
         for (uint32_t x0 = 0; x0 < tw; x0 += 32) {
             const uint32_t x = x0 + lane;
-            int32_t v = x < tw ? delta[y * gw + x] : 0;
+            int32_t v = x < tw ? g[(size_t)(y * gw + x) * gs] : 0;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 const int32_t t = __shfl_up_sync(0xffffffffu, v, off);
                 if (lane >= off) v += t;
             }
             v += carry;
-            if (x < tw) delta[y * gw + x] = v;
+            if (x < tw) g[(size_t)(y * gw + x) * gs] = v;
             carry = __shfl_sync(0xffffffffu, v, 31);
         }
     }
@@ -136,9 +143,9 @@ __device__ void bin_counts_of_camera(int32_t *delta, uint32_t tw, uint32_t th, i
     for (uint32_t x = threadIdx.x; x < tw; x += kScanThreads) {
         int32_t acc = 0;
         for (uint32_t y0 = 0; y0 < th; y0 += 8) {
-            int32_t d[8];  // independent loads first: the running sum must not serialise eight L2 round trips
+            int32_t d[8];  // independent loads first: the running sum must not serialise eight round trips
 #pragma unroll
-            for (int k = 0; k < 8; ++k) d[k] = y0 + k < th ? delta[(y0 + k) * gw + x] : 0;
+            for (int k = 0; k < 8; ++k) d[k] = y0 + k < th ? g[(size_t)((y0 + k) * gw + x) * gs] : 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if (y0 + k < th) {
@@ -170,7 +177,7 @@ __device__ void bin_offsets_of_camera(uint32_t cam, uint32_t C, uint32_t n_tiles
             const int64_t excl = base + incl - cnt;
             const int32_t o = (int32_t)(excl < capacity ? excl : capacity);
             offsets[t] = o;
-            cursor[t] = o;
+            cursor[(size_t)t * kCursorStride] = o;
         }
         base += tot;
     }
@@ -183,15 +190,28 @@ __device__ void bin_offsets_of_camera(uint32_t cam, uint32_t C, uint32_t n_tiles
 __global__ void __launch_bounds__(kScanThreads)
 bin_scan_kernel(uint32_t C, uint32_t tw, uint32_t th, int64_t capacity, int32_t *__restrict__ delta,
                 int32_t *__restrict__ offsets, int32_t *__restrict__ cursor, int64_t *__restrict__ cam_total,
-                int64_t *__restrict__ n_isects, int32_t *__restrict__ status, int phase) {
+                int64_t *__restrict__ n_isects, int32_t *__restrict__ status, int phase, int grid_in_smem) {
+    extern __shared__ int32_t s_grid[];  // th * tw ints when grid_in_smem
     __shared__ int64_t s_warp[kScanThreads / 32];
     const uint32_t cam = blockIdx.x, n_tiles = tw * th;
-    if (phase != 2) bin_counts_of_camera(delta + (size_t)cam * (th + 1) * (tw + 1), tw, th, offsets + (size_t)cam * n_tiles,
-                                         cam_total + cam, s_warp);
+    if (phase != 2) {
+        int32_t *d = delta + (size_t)cam * (th + 1) * (tw + 1) * kDeltaStride;
+        if (grid_in_smem) {
+            for (uint32_t i = threadIdx.x; i < n_tiles; i += kScanThreads) {
+                const uint32_t y = i / tw, x = i - y * tw;
+                s_grid[i] = d[(size_t)(y * (tw + 1) + x) * kDeltaStride];
+            }
+            __syncthreads();
+            bin_counts_of_camera(s_grid, tw, 1, tw, th, offsets + (size_t)cam * n_tiles, cam_total + cam, s_warp);
+        } else {
+            bin_counts_of_camera(d, tw + 1, kDeltaStride, tw, th, offsets + (size_t)cam * n_tiles, cam_total + cam,
+                                 s_warp);
+        }
+    }
     // a single camera needs no second launch: its total is already visible to this CTA
     if (phase == 2 || C == 1)
         bin_offsets_of_camera(cam, C, n_tiles, cam_total, capacity, offsets + (size_t)cam * n_tiles,
-                              cursor + (size_t)cam * n_tiles, n_isects, status, s_warp);
+                              cursor + (size_t)cam * n_tiles * kCursorStride, n_isects, status, s_warp);
 }
 
 // ---- emit: every pair goes straight into its tile's segment --------------------------------------------------
@@ -207,12 +227,27 @@ bin_emit_kernel(int64_t CN, int64_t N, const float *__restrict__ means2d, const 
     const TileRect t = tile_rect(m.x, m.y, r, tile_size, tile_width, tile_height);
     if (t.x1 <= t.x0 || t.y1 <= t.y0) return;
     const uint64_t kv = ((uint64_t)__float_as_uint(depths[idx]) << 32) | (uint64_t)(uint32_t)idx;
-    int32_t *cur = cursor + (idx / N) * (int64_t)(tile_width * tile_height);
-    for (uint32_t i = t.y0; i < t.y1; ++i) {
-        for (uint32_t j = t.x0; j < t.x1; ++j) {
-            const int32_t pos = atomicAdd(cur + i * tile_width + j, 1);
-            if ((int64_t)(uint32_t)pos < capacity) keyval[(uint32_t)pos] = kv;
+    int32_t *cur = cursor + (idx / N) * (int64_t)(tile_width * tile_height) * kCursorStride;
+    // four slot reservations in flight before the first dependent store: the returning atomics are what this
+    // kernel waits on (long-scoreboard stalls, 13 % issue utilisation when issued one at a time)
+    const uint32_t cnt = (t.x1 - t.x0) * (t.y1 - t.y0);
+    uint32_t tx = t.x0, ty = t.y0;
+    for (uint32_t k0 = 0; k0 < cnt; k0 += 4) {
+        uint32_t pos[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            pos[q] = 0xffffffffu;
+            if (k0 + q < cnt) {
+                pos[q] = (uint32_t)atomicAdd(cur + (size_t)(ty * tile_width + tx) * kCursorStride, 1);
+                if (++tx == t.x1) {
+                    tx = t.x0;
+                    ++ty;
+                }
+            }
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if ((int64_t)pos[q] < capacity) keyval[pos[q]] = kv;
     }
 }
 
@@ -274,16 +309,105 @@ __device__ __forceinline__ uint32_t warp_rank_digit(uint32_t d, bool valid, uint
     return prev + __popc(peers & ((1u << lane) - 1u));
 }
 
-__global__ void __launch_bounds__(kSegThreads)
+// One stable LSD pass over BITS key bits of a segment held in shared memory as 64-bit words key << 32 | id.
+//   * peer sets from BITS ballots (4 instructions per bit: sign mask, predicate, VOTE, LOP3);
+//   * per-warp digit counters -> (thread per digit, or per digit pair when BITS == 9) exclusive offsets over warps,
+//     one block scan, segment-wide digit bases folded back into the per-warp counters, so the scatter position is
+//     one shared load + the in-warp rank.
+struct SegSmem {
+    unsigned long long kv[2][kSegMax];       // 32 KB
+    __align__(16) uint32_t cnt[kSegWarps * 512];  // 16 KB
+    uint32_t tmp[kSegWarps];
+    uint32_t wmin[kSegWarps], wmax[kSegWarps];
+};
+
+template <int BITS>
+__device__ __noinline__ void segment_radix_pass(SegSmem &sm, int cur, int shift, int32_t n, int32_t chunk) {
+    constexpr int NDIG = 1 << BITS;
+    constexpr int PER = NDIG > kSegThreads ? NDIG / kSegThreads : 1;  // digits per thread in the prefix step
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = (int)tid; i < kSegWarps * NDIG / 4; i += kSegThreads)
+        reinterpret_cast<uint4 *>(sm.cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    uint32_t *my_cnt = sm.cnt + warp * NDIG;
+    const int32_t wbase = (int32_t)warp * chunk;
+    uint32_t rank2[kSegItems / 2];  // two 16-bit in-warp ranks per register (a rank is < kSegMax)
+#pragma unroll
+    for (int it = 0; it < kSegItems / 2; ++it) rank2[it] = 0;
+#pragma unroll
+    for (int it = 0; it < kSegItems; ++it) {
+        if (it * 32 < chunk) {
+            const int32_t e = wbase + it * 32 + (int32_t)lane;
+            const bool valid = e < n;
+            const uint32_t key = valid ? (uint32_t)(sm.kv[cur][e] >> 32) : 0u;
+            const uint32_t d = (key >> shift) & (uint32_t)(NDIG - 1);
+            uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+            for (int b = 0; b < BITS; ++b) {
+                const uint32_t sgn = (uint32_t)((int32_t)(d << (31 - b)) >> 31);  // all ones iff bit b of d is set
+                const uint32_t m = __ballot_sync(0xffffffffu, sgn != 0u);
+                peers &= ~(m ^ sgn);                                               // bit ? m : ~m
+            }
+            const int leader = __ffs(peers) - 1;
+            uint32_t prev = 0;
+            if ((int)lane == leader && valid) {
+                prev = my_cnt[d];
+                my_cnt[d] = prev + __popc(peers);
+            }
+            prev = __shfl_sync(0xffffffffu, prev, leader);
+            __syncwarp();
+            rank2[it >> 1] |= (prev + __popc(peers & ((1u << lane) - 1u))) << (16 * (it & 1));
+        }
+    }
+    __syncthreads();
+    // digits of this thread: counts of the warps -> exclusive offsets over warps; segment-wide digit totals
+    uint32_t tot[PER], sum = 0;
+    if (tid * PER < NDIG) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int d = (int)tid * PER + q;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int w = 0; w < kSegWarps; ++w) {
+                const uint32_t c = sm.cnt[w * NDIG + d];
+                sm.cnt[w * NDIG + d] = acc;
+                acc += c;
+            }
+            tot[q] = acc;
+            sum += acc;
+        }
+    }
+    uint32_t base = block_exclusive_scan_u32_256(sum, sm.tmp);  // contains two barriers
+    if (tid * PER < NDIG) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int d = (int)tid * PER + q;
+#pragma unroll
+            for (int w = 0; w < kSegWarps; ++w) sm.cnt[w * NDIG + d] += base;
+            base += tot[q];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kSegItems; ++it) {
+        if (it * 32 < chunk) {
+            const int32_t e = wbase + it * 32 + (int32_t)lane;
+            if (e < n) {
+                const unsigned long long kv = sm.kv[cur][e];
+                const uint32_t d = ((uint32_t)(kv >> 32) >> shift) & (uint32_t)(NDIG - 1);
+                sm.kv[cur ^ 1][my_cnt[d] + ((rank2[it >> 1] >> (16 * (it & 1))) & 0xffffu)] = kv;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSegThreads, 4)
 segment_sort_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits, const int32_t *__restrict__ offsets,
                     const int64_t *__restrict__ n_isects_dev, int64_t capacity, const uint64_t *__restrict__ keyval,
                     int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
-    __shared__ uint32_t s_key[2][kSegMax];
-    __shared__ uint32_t s_id[2][kSegMax];
-    __shared__ uint32_t s_cnt[kSegWarps * 256];
-    __shared__ uint32_t s_base[256];
-    __shared__ uint32_t s_tmp[kSegWarps];
-    __shared__ uint32_t s_min[kSegWarps], s_max[kSegWarps];
+    extern __shared__ __align__(16) unsigned char seg_smem_raw[];
+    SegSmem &sm = *reinterpret_cast<SegSmem *>(seg_smem_raw);
 
     const int64_t n_total = min(*n_isects_dev, capacity);
     const SegRange seg = segment_of(blockIdx.x, n_slots, n_tiles, tile_n_bits, offsets, n_total);
@@ -292,94 +416,75 @@ segment_sort_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits, co
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t *src = keyval + seg.start;
 
-    // ---- load, depth range of the segment ---------------------------------------------------------------------
+    // ---- depth range of the segment; keys are stored relative to the smallest one ------------------------------
+    unsigned long long mine[kSegItems];
     uint32_t kmin = 0xffffffffu, kmax = 0u;
-    for (int32_t i = (int32_t)tid; i < n; i += kSegThreads) {
-        const uint64_t kv = src[i];
-        const uint32_t k = (uint32_t)(kv >> 32);
-        s_key[0][i] = k;
-        s_id[0][i] = (uint32_t)kv;
-        kmin = min(kmin, k);
-        kmax = max(kmax, k);
+#pragma unroll
+    for (int it = 0; it < kSegItems; ++it) {
+        const int32_t i = it * kSegThreads + (int32_t)tid;
+        if (i < n) {
+            mine[it] = src[i];
+            const uint32_t k = (uint32_t)(mine[it] >> 32);
+            kmin = min(kmin, k);
+            kmax = max(kmax, k);
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, off));
         kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, off));
     }
-    if (lane == 0) s_min[warp] = kmin, s_max[warp] = kmax;
+    if (lane == 0) sm.wmin[warp] = kmin, sm.wmax[warp] = kmax;
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < kSegWarps; ++w) {
-        kmin = min(kmin, s_min[w]);
-        kmax = max(kmax, s_max[w]);
+        kmin = min(kmin, sm.wmin[w]);
+        kmax = max(kmax, sm.wmax[w]);
     }
     const uint32_t lo = kmin;
+#pragma unroll
+    for (int it = 0; it < kSegItems; ++it) {
+        const int32_t i = it * kSegThreads + (int32_t)tid;
+        if (i < n) sm.kv[0][i] = mine[it] - ((unsigned long long)lo << 32);
+    }
     const int nbits = 32 - __clz(kmax - kmin);  // 0 when every depth is identical
-    const int passes = (nbits + 7) >> 3;
+    const int passes = (nbits + 8) / 9;         // digits of at most 9 bits
+    const int width = passes > 0 ? (nbits + passes - 1) / passes : 0;
+    __syncthreads();
 
     // each warp owns a contiguous chunk (a multiple of 32 elements); order inside = (item, lane)
     const int32_t chunk = ((n + kSegThreads - 1) / kSegThreads) * 32;
-    const int32_t wbase = (int32_t)warp * chunk;
-    uint32_t *my_cnt = s_cnt + warp * 256;
     int cur = 0;
-
     for (int p = 0; p < passes; ++p) {
-        const int shift = 8 * p;
-#pragma unroll
-        for (int k = 0; k < kSegWarps; ++k) s_cnt[k * 256 + tid] = 0;
-        __syncthreads();
-        uint32_t key[kSegItems], rank[kSegItems];
-#pragma unroll
-        for (int it = 0; it < kSegItems; ++it) {
-            if (it * 32 < chunk) {
-                const int32_t e = wbase + it * 32 + (int32_t)lane;
-                const bool valid = e < n;
-                key[it] = valid ? s_key[cur][e] : 0u;
-                const uint32_t d = valid ? (((key[it] - lo) >> shift) & 255u) : 0u;
-                rank[it] = warp_rank_digit(d, valid, my_cnt, lane);
-            }
+        const int shift = p * width;
+        switch (width) {  // uniform across the CTA
+            case 1: segment_radix_pass<1>(sm, cur, shift, n, chunk); break;
+            case 2: segment_radix_pass<2>(sm, cur, shift, n, chunk); break;
+            case 3: segment_radix_pass<3>(sm, cur, shift, n, chunk); break;
+            case 4: segment_radix_pass<4>(sm, cur, shift, n, chunk); break;
+            case 5: segment_radix_pass<5>(sm, cur, shift, n, chunk); break;
+            case 6: segment_radix_pass<6>(sm, cur, shift, n, chunk); break;
+            case 7: segment_radix_pass<7>(sm, cur, shift, n, chunk); break;
+            case 8: segment_radix_pass<8>(sm, cur, shift, n, chunk); break;
+            default: segment_radix_pass<9>(sm, cur, shift, n, chunk); break;
         }
-        __syncthreads();
-        // digit `tid`: counts of the warps -> exclusive offsets of the warps, segment-wide count
-        uint32_t cnt_d = 0;
-#pragma unroll
-        for (int w = 0; w < kSegWarps; ++w) {
-            const uint32_t c = s_cnt[w * 256 + tid];
-            s_cnt[w * 256 + tid] = cnt_d;
-            cnt_d += c;
-        }
-        s_base[tid] = block_exclusive_scan_u32_256(cnt_d, s_tmp);
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < kSegItems; ++it) {
-            if (it * 32 < chunk) {
-                const int32_t e = wbase + it * 32 + (int32_t)lane;
-                if (e < n) {
-                    const uint32_t d = ((key[it] - lo) >> shift) & 255u;
-                    const uint32_t pos = s_base[d] + my_cnt[d] + rank[it];
-                    s_key[cur ^ 1][pos] = key[it];
-                    s_id[cur ^ 1][pos] = s_id[cur][e];
-                }
-            }
-        }
-        __syncthreads();
         cur ^= 1;
     }
 
     // ---- write out; bit-identical depths are ordered by flatten id (each element ranks itself in its run) ------
-    const uint32_t *K = s_key[cur], *I = s_id[cur];
+    const unsigned long long *S = sm.kv[cur];
     int64_t *out_keys = isect_ids + seg.start;
     int32_t *out_vals = flatten_ids + seg.start;
     for (int32_t i = (int32_t)tid; i < n; i += kSegThreads) {
-        const uint32_t k = K[i], id = I[i];
+        const unsigned long long kv = S[i];
+        const uint32_t k = (uint32_t)(kv >> 32), id = (uint32_t)kv;
         int32_t a = i, less = 0;
-        while (a > 0 && K[a - 1] == k) {
+        while (a > 0 && (uint32_t)(S[a - 1] >> 32) == k) {
             --a;
-            less += I[a] < id;
+            less += (uint32_t)S[a] < id;
         }
-        for (int32_t j = i + 1; j < n && K[j] == k; ++j) less += I[j] < id;
-        out_keys[a + less] = (int64_t)(seg.hi | (uint64_t)k);
+        for (int32_t j = i + 1; j < n && (uint32_t)(S[j] >> 32) == k; ++j) less += (uint32_t)S[j] < id;
+        out_keys[a + less] = (int64_t)(seg.hi | (uint64_t)(k + lo));
         out_vals[a + less] = (int32_t)id;
     }
 }
@@ -397,10 +502,22 @@ segment_sort_big_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits
     __shared__ unsigned long long s_or[kSegWarps];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n_total = min(*n_isects_dev, capacity);
-    for (uint32_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+    // each CTA owns a contiguous range of slots and first finds the long ones with all threads in parallel
+    __shared__ uint32_t s_long[kSegThreads];
+    __shared__ uint32_t s_n_long;
+    const uint32_t per_cta = (n_slots + gridDim.x - 1) / gridDim.x;
+    const uint32_t slot_begin = blockIdx.x * per_cta, slot_end = min(n_slots, slot_begin + per_cta);
+    for (uint32_t s0 = slot_begin; s0 < slot_end; s0 += kSegThreads) {
+      if (tid == 0) s_n_long = 0;
+      __syncthreads();
+      if (s0 + tid < slot_end && segment_of(s0 + tid, n_slots, n_tiles, tile_n_bits, offsets, n_total).n > kSegMax)
+          s_long[atomicAdd(&s_n_long, 1u)] = s0 + tid;
+      __syncthreads();
+      const uint32_t n_long = s_n_long;
+      for (uint32_t li = 0; li < n_long; ++li) {
+        const uint32_t slot = s_long[li];
         const SegRange seg = segment_of(slot, n_slots, n_tiles, tile_n_bits, offsets, n_total);
         const int32_t n = seg.n;
-        if (n <= kSegMax) continue;
         uint64_t *src = keyval + seg.start, *dst = alt + seg.start;
         // bits that differ anywhere in the segment
         const uint64_t first = src[0];
@@ -458,6 +575,7 @@ segment_sort_big_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits
             flatten_ids[seg.start + i] = (int32_t)(uint32_t)kv;
         }
         __syncthreads();
+      }
     }
 }
 
@@ -515,14 +633,22 @@ extern "C" int ubs_isect_bin_sort(int C, int64_t N, const float *means2d, const 
             UBS_LAUNCH_CHECK("bin_count_kernel");
         }
     }
-    bin_scan_kernel<<<(unsigned)C, kScanThreads, 0, s>>>((uint32_t)C, (uint32_t)tile_width, (uint32_t)tile_height,
-                                                         capacity, w.delta, offsets, w.cursor, w.cam_total, n_isects,
-                                                         status, 1);
+    // the camera's tile grid is staged in shared memory when it fits (up to 160 KB = 40960 tiles)
+    const size_t grid_smem = sizeof(int32_t) * (size_t)n_tiles;
+    const int in_smem = grid_smem <= 160 * 1024 ? 1 : 0;
+    static size_t scan_smem_set = 0;
+    if (in_smem && grid_smem > 48 * 1024 && grid_smem > scan_smem_set) {
+        UBS_CUDA_TRY(cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        scan_smem_set = 160 * 1024;
+    }
+    bin_scan_kernel<<<(unsigned)C, kScanThreads, in_smem ? grid_smem : 0, s>>>(
+        (uint32_t)C, (uint32_t)tile_width, (uint32_t)tile_height, capacity, w.delta, offsets, w.cursor, w.cam_total,
+        n_isects, status, 1, in_smem);
     UBS_LAUNCH_CHECK("bin_scan_kernel");
     if (C > 1) {
         bin_scan_kernel<<<(unsigned)C, kScanThreads, 0, s>>>((uint32_t)C, (uint32_t)tile_width, (uint32_t)tile_height,
                                                              capacity, w.delta, offsets, w.cursor, w.cam_total,
-                                                             n_isects, status, 2);
+                                                             n_isects, status, 2, 0);
         UBS_LAUNCH_CHECK("bin_scan_kernel");
     }
     if (CN == 0 || capacity == 0) return UBS_OK;
@@ -530,7 +656,13 @@ extern "C" int ubs_isect_bin_sort(int C, int64_t N, const float *means2d, const 
         CN, N, means2d, radii, depths, (uint32_t)tile_size, (uint32_t)tile_width, (uint32_t)tile_height, capacity,
         w.cursor, w.keyval);
     UBS_LAUNCH_CHECK("bin_emit_kernel");
-    segment_sort_kernel<<<n_slots, kSegThreads, 0, s>>>(n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects,
+    static bool seg_attr_set = false;
+    if (!seg_attr_set) {
+        UBS_CUDA_TRY(cudaFuncSetAttribute(segment_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SegSmem)));
+        seg_attr_set = true;
+    }
+    segment_sort_kernel<<<n_slots, kSegThreads, sizeof(SegSmem), s>>>(n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects,
                                                         capacity, w.keyval, isect_ids, flatten_ids);
     UBS_LAUNCH_CHECK("segment_sort_kernel");
     int sm = ubs_device_sm_count();

@@ -30,12 +30,15 @@ __device__ __forceinline__ TileRect tile_rect(float mx, float my, int32_t radius
 // Tile binning (bin_sort.cu): a primitive covering tiles [x0,x1) x [y0,y1) adds +1/-1 at the four corners of that
 // rectangle in the camera's (tile_height+1) x (tile_width+1) delta grid; the 2-D prefix sum of the grid is the
 // number of pairs per tile.
+// Cells are kDeltaStride ints apart (one per 32-byte sector): packed 4-byte cells put the whole grid into a few
+// L2 slices whose atomic units then saturate.
+constexpr int kDeltaStride = 8;
 __device__ __forceinline__ void add_tile_deltas(int32_t *delta, const TileRect &t, uint32_t tile_width) {
     const uint32_t gw = tile_width + 1;
-    atomicAdd(delta + t.y0 * gw + t.x0, 1);
-    atomicAdd(delta + t.y0 * gw + t.x1, -1);
-    atomicAdd(delta + t.y1 * gw + t.x0, -1);
-    atomicAdd(delta + t.y1 * gw + t.x1, 1);
+    atomicAdd(delta + (size_t)(t.y0 * gw + t.x0) * kDeltaStride, 1);
+    atomicAdd(delta + (size_t)(t.y0 * gw + t.x1) * kDeltaStride, -1);
+    atomicAdd(delta + (size_t)(t.y1 * gw + t.x0) * kDeltaStride, -1);
+    atomicAdd(delta + (size_t)(t.y1 * gw + t.x1) * kDeltaStride, 1);
 }
 
 // Block-wide (kIsectThreads) int64 sum; result valid in thread 0.
