@@ -151,6 +151,7 @@ __device__ void bin_counts_of_camera(int32_t *g, uint32_t gw, uint32_t gs, uint3
                 if (y0 + k < th) {
                     acc += d[k];
                     counts[(y0 + k) * tw + x] = acc;
+                    g[(size_t)((y0 + k) * gw + x) * gs] = acc;  // kept for the offsets phase (shared-memory path)
                     mine += acc;
                 }
             }
@@ -187,6 +188,27 @@ __device__ void bin_offsets_of_camera(uint32_t cam, uint32_t C, uint32_t n_tiles
     }
 }
 
+// Phase 2, single camera with the counts still in shared memory: every thread owns a run of consecutive tiles, so the
+// whole exclusive scan needs ONE block scan and no global reads.
+__device__ void bin_offsets_from_smem(const int32_t *cnt, uint32_t n_tiles, int64_t capacity, int32_t *offsets,
+                                      int32_t *cursor, int64_t *n_isects, int32_t *status, int64_t *s_warp) {
+    const uint32_t per = (n_tiles + kScanThreads - 1) / kScanThreads;
+    const uint32_t t0 = threadIdx.x * per, t1 = min(n_tiles, t0 + per);
+    int64_t mine = 0, total;
+    for (uint32_t t = t0; t < t1; ++t) mine += cnt[t];
+    int64_t run = block_inclusive_scan_i64(mine, s_warp, &total) - mine;
+    for (uint32_t t = t0; t < t1; ++t) {
+        const int32_t o = (int32_t)(run < capacity ? run : capacity);
+        offsets[t] = o;
+        cursor[(size_t)t * kCursorStride] = o;
+        run += cnt[t];
+    }
+    if (threadIdx.x == 0) {
+        *n_isects = total;
+        if (total > capacity && status != nullptr) atomicOr(status, 1);
+    }
+}
+
 __global__ void __launch_bounds__(kScanThreads)
 bin_scan_kernel(uint32_t C, uint32_t tw, uint32_t th, int64_t capacity, int32_t *__restrict__ delta,
                 int32_t *__restrict__ offsets, int32_t *__restrict__ cursor, int64_t *__restrict__ cam_total,
@@ -209,6 +231,10 @@ bin_scan_kernel(uint32_t C, uint32_t tw, uint32_t th, int64_t capacity, int32_t 
         }
     }
     // a single camera needs no second launch: its total is already visible to this CTA
+    if (phase != 2 && C == 1 && grid_in_smem) {
+        bin_offsets_from_smem(s_grid, n_tiles, capacity, offsets, cursor, n_isects, status, s_warp);
+        return;
+    }
     if (phase == 2 || C == 1)
         bin_offsets_of_camera(cam, C, n_tiles, cam_total, capacity, offsets + (size_t)cam * n_tiles,
                               cursor + (size_t)cam * n_tiles * kCursorStride, n_isects, status, s_warp);

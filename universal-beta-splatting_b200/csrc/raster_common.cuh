@@ -60,4 +60,18 @@ __device__ __forceinline__ float4 support_bbox(float mx, float my, float a, floa
     }
     return make_float4(mx - hx, mx + hx, my - hy, my + hy);
 }
+
+// Which of the tile's eight 8x4 sub-tiles (bit w = warp w: column w & 1, row w >> 1; see sub_tile_of) can the
+// sigma < 1 box `bb` = (xmin, xmax, ymin, ymax) touch.  (tx0, ty0) = centre of the tile's first pixel.  Computed once
+// per staged pair by the staging thread; each warp then only tests its bit.
+__device__ __forceinline__ uint32_t sub_tile_mask(float4 bb, float tx0, float ty0) {
+    uint32_t mx = 0, my = 0;
+    if (bb.x <= tx0 + 7.f && bb.y >= tx0) mx |= 0x55u;
+    if (bb.x <= tx0 + 15.f && bb.y >= tx0 + 8.f) mx |= 0xAAu;
+    if (bb.z <= ty0 + 3.f && bb.w >= ty0) my |= 0x03u;
+    if (bb.z <= ty0 + 7.f && bb.w >= ty0 + 4.f) my |= 0x0Cu;
+    if (bb.z <= ty0 + 11.f && bb.w >= ty0 + 8.f) my |= 0x30u;
+    if (bb.z <= ty0 + 15.f && bb.w >= ty0 + 12.f) my |= 0xC0u;
+    return mx & my;
+}
 }  // namespace ubs

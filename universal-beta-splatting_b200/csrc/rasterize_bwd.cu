@@ -293,13 +293,12 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
     if (num_batches <= 0) return;
 
     __shared__ Staged3 s_rec[kTilePixels + 1];  // [kTilePixels] = sentinel (sigma = NaN) padding the lists
-    __shared__ float4 s_bbox[kTilePixels];
+    __shared__ uint8_t s_mask[kTilePixels];  // sub-tiles the sigma < 1 box of each staged pair can touch
     __shared__ int32_t s_id[kTilePixels];
     __shared__ float s_acc[kTilePixels * kAccStride];
     __shared__ __align__(8) uint16_t s_list[kTilePixels / 32][kTilePixels + 4];
 
-    const float wx0 = (float)(blockIdx.x * kTile + st.bx * kSubW) + 0.5f, wx1 = wx0 + (float)(kSubW - 1);
-    const float wy0 = (float)(blockIdx.y * kTile + st.by * kSubH) + 0.5f, wy1 = wy0 + (float)(kSubH - 1);
+    const float tx0 = (float)(blockIdx.x * kTile) + 0.5f, ty0 = (float)(blockIdx.y * kTile) + 0.5f;  // first pixel centre
     uint16_t *my_list = s_list[warp];
     const uint32_t rec_addr = smem_addr(s_rec), list_addr = smem_addr(my_list);
     const float kNaN = __int_as_float(0x7fffffff);
@@ -381,7 +380,7 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
             s_rec[tr].xyob = make_float4(xy.x, xy.y, opacities[g], betas[g]);
             s_rec[tr].conic = make_float4(ca, cb + cb, cc, 0.f);
             s_rec[tr].col = make_float4(colors[(size_t)g * 3], colors[(size_t)g * 3 + 1], colors[(size_t)g * 3 + 2], 0.f);
-            s_bbox[tr] = support_bbox(xy.x, xy.y, ca, cb, cc);
+            s_mask[tr] = (uint8_t)sub_tile_mask(support_bbox(xy.x, xy.y, ca, cb, cc), tx0, ty0);
         }
         __syncthreads();
 
@@ -392,11 +391,7 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
         uint32_t cnt = 0;
         for (int32_t p0 = t_begin & ~31; p0 < batch_size; p0 += 32) {
             const int32_t p = p0 + (int32_t)lane;
-            bool hit = false;
-            if (p >= t_begin && p < batch_size) {
-                const float4 bb = s_bbox[p];
-                hit = (bb.x <= wx1) && (bb.y >= wx0) && (bb.z <= wy1) && (bb.w >= wy0);
-            }
+            const bool hit = p >= t_begin && p < batch_size && ((s_mask[p] >> warp) & 1u);
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
             if (hit) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(p * kRec);
             cnt += __popc(m);

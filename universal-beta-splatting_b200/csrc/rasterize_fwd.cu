@@ -13,7 +13,7 @@ namespace ubs {
 namespace {
 
 template <int CH>
-__global__ void __launch_bounds__(kTilePixels)
+__global__ void __launch_bounds__(kTilePixels, CH <= 4 ? 5 : 2)
 rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev, int64_t isect_capacity,
                      const float2 *__restrict__ means2d, const float *__restrict__ conics,
                      const float *__restrict__ colors, const float *__restrict__ opacities,
@@ -63,13 +63,11 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
     constexpr int kUnroll = 4;
     static_assert((kTilePixels + 1) * sizeof(Staged) <= 65535, "staged-record offsets must fit 16 bits");
     __shared__ Staged s_rec[kTilePixels + 1];  // [kTilePixels] = sentinel whose sigma is NaN (pads the lists)
-    __shared__ float4 s_bbox[kTilePixels];     // xmin, xmax, ymin, ymax of the sigma < 1 ellipse (inflated)
+    __shared__ uint8_t s_mask[kTilePixels];    // sub-tiles the (inflated) sigma < 1 box of each staged pair can touch
     // per-warp compacted lists of byte offsets into s_rec, padded to a multiple of kUnroll with the sentinel
     __shared__ __align__(8) uint16_t s_list[kTilePixels / 32][kTilePixels + kUnroll];
 
-    // pixel-centre rectangle of this warp's 8x4 sub-tile
-    const float wx0 = (float)(blockIdx.x * kTile + st.bx * kSubW) + 0.5f, wx1 = wx0 + (float)(kSubW - 1);
-    const float wy0 = (float)(blockIdx.y * kTile + st.by * kSubH) + 0.5f, wy1 = wy0 + (float)(kSubH - 1);
+    const float tx0 = (float)(blockIdx.x * kTile) + 0.5f, ty0 = (float)(blockIdx.y * kTile) + 0.5f;  // first pixel centre
     const uint32_t lane = tr & 31, warp = tr >> 5;
     uint16_t *my_list = s_list[warp];
     const uint32_t rec_addr = smem_addr(s_rec), list_addr = smem_addr(my_list);
@@ -110,7 +108,7 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         // everyone has finished reading the previous batch; stop when every pixel of the tile is done
         if (__syncthreads_count(T < 0.f) >= kTilePixels) break;
         s_rec[tr].xyob = r_xyob;
-        s_bbox[tr] = support_bbox(r_xyob.x, r_xyob.y, r_conic.x, r_conic.y, r_conic.z);
+        s_mask[tr] = (uint8_t)sub_tile_mask(support_bbox(r_xyob.x, r_xyob.y, r_conic.x, r_conic.y, r_conic.z), tx0, ty0);
         s_rec[tr].conic = make_float4(r_conic.x, r_conic.y + r_conic.y, r_conic.z, 0.f);  // b + b as the reference forms it
         if constexpr (kPacked) {
             *reinterpret_cast<float4 *>(s_rec[tr].col) = make_float4(r_color[0], r_color[1], r_color[2], r_color[3]);
@@ -129,11 +127,7 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         uint32_t cnt = 0;
         for (int32_t p0 = 0; p0 < batch_size; p0 += 32) {
             const int32_t p = p0 + (int32_t)lane;
-            bool hit = false;
-            if (p < batch_size) {
-                const float4 bb = s_bbox[p];
-                hit = (bb.x <= wx1) && (bb.y >= wx0) && (bb.z <= wy1) && (bb.w >= wy0);
-            }
+            const bool hit = p < batch_size && ((s_mask[p] >> warp) & 1u);
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
             if (hit) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(p * (int32_t)sizeof(Staged));
             cnt += __popc(m);
