@@ -384,8 +384,14 @@ def run_ours(args, rank, local_rank, world):
                                 "unit": "GB/s", "frac": a / hbm_peak, "traffic": traffic.get(name)}
 
     hbm_stage("fused_project_fwd", stages.get("fused_project_fwd", (0, float("nan")))[1], N * rec_b + vis * 36)
+    # SURVEY 8(d) unit figure: emit 12 B/pair + onesweep I (8 + 24 p) + offsets 8 B/pair.  The tile-binning route
+    # this library runs (csrc/bin_sort.cu) moves 28 B/pair (8 written, 8 read, 12 written) and is bound by the
+    # ranking instructions of its per-tile shared-memory sort, not by HBM; both figures are reported.
     hbm_stage("isect_emit_sort_offsets", stages.get("isect_emit_sort_offsets", (0, float("nan")))[1],
               pairs * (12 + 8 + 24 * passes + 8))
+    if "isect_emit_sort_offsets" in stage_roof:
+        stage_roof["isect_emit_sort_offsets"]["route"] = rz.sort_mode
+        stage_roof["isect_emit_sort_offsets"]["bytes_moved_by_bin_route"] = pairs * 28
     hbm_stage("fused_project_bwd", stages_train.get("fused_project_bwd", (0, float("nan")))[1],
               2 * N * rec_b + vis * 76)
     stage_roof["rasterize_bwd"] = {"bound": "fp32", "ms": stages_train.get("rasterize_bwd", (0, float("nan")))[1],
@@ -414,7 +420,8 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": desc, "name": args.workload, "N": N, "D": D, "width": W, "height": H,
                    "cameras_per_gpu_per_step": 1, "parallelism": "camera-parallel x%d, no collective" % world,
                    "l2": "inputs larger than L2 (%.0f MB parameter records re-read every step)" % (N * rec_b / 1e6),
-                   "pairs_per_frame": pairs, "visible_per_frame": vis, "peak_source": peak_src},
+                   "pairs_per_frame": pairs, "visible_per_frame": vis, "peak_source": peak_src,
+                   "sort_route": rz.sort_mode},
         "train": {"metric": "train_it_per_s", "value": its, "unit": "it/s", "ms_per_step": ms_train / args.steps,
                   "what": "forward + backward to the packed parameter-gradient records" +
                           (" + NCCL allreduce(sum) of the %.0f MB gradient buffer" % (N * rec_b / 1e6)
