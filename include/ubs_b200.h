@@ -249,6 +249,37 @@ int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const f
                           float *v_records,                                                       /* [N, stride] */
                           void *stream);
 
+/* ---- the train step around the render --------------------------------------------- */
+/* Photometric loss and its gradient: (1 - lambda) * mean|img - gt| + lambda * (1 - mean SSIM(img, gt)).
+ * replaces l1_loss + fused_ssim + autograd (train.py:118-121; utils/loss_utils.py:18-19,45-85; fused_ssim is the
+ * third-party rahul-goel/fused-ssim@1272e21 of setup.py:26 -- same 11x11 sigma-1.5 zero-padded window).
+ * Images are addressed by element strides (n, channel, y, x), so the rendered [C,H,W,ch] buffer and a [ch,H,W]
+ * ground-truth image are both read in place; v_img is written with img's strides.
+ * loss_out: NULL or [3] device floats = {L1, SSIM, loss}.  v_img: NULL (evaluate only) or d(grad_scale * loss)/d img.
+ * workspace: ubs_l1_ssim_workspace_bytes() bytes (16 suffice when v_img == NULL).                             */
+size_t ubs_l1_ssim_workspace_bytes(int C, int channels, int height, int width);
+int ubs_l1_ssim_loss(int C, int channels, int height, int width, const float *img, int64_t img_sn, int64_t img_sc,
+                     int64_t img_sy, int64_t img_sx, const float *gt, int64_t gt_sn, int64_t gt_sc, int64_t gt_sy,
+                     int64_t gt_sx, float lambda_dssim, float grad_scale, float *loss_out, float *v_img,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* torch.optim.Adam(eps) over the packed records, one learning rate per record column (h_lr: HOST array of
+ * UBS_RECORD_STRIDE(D) doubles; padding columns are never moved).  replaces optimizer.step() over the seven
+ * parameter groups of scene/beta_model.py:239-268 (train.py:169).  `step` counts from 1.  opacity_reg / scale_reg
+ * != 0 add the gradient of  opacity_reg * mean|sigmoid(raw opacity)| + scale_reg * mean|softplus(raw scale)[:3]|
+ * (train.py:122-124; `[:3]` selects the first three primitives there and here).                               */
+int ubs_adam_step(int64_t N, int D, float *records, const float *grads, float *exp_avg, float *exp_avg_sq,
+                  const double *h_lr, double beta1, double beta2, double eps, int64_t step, double opacity_reg,
+                  double scale_reg, void *stream);
+
+/* MCMC relocation given the sampled indices: rows dst_idx[i] <- rows src_idx[i] with the opacity rescaled to
+ * 1 - (1 - o)^(1/(m+1)), m = multiplicity of the source among src_idx, clamped to [0.005, 1 - eps]; the sources
+ * take the same opacity and their Adam moments are zeroed (exp_avg / exp_avg_sq may both be NULL).
+ * replaces the tensor part of relocate_gs / add_new_gs (scene/beta_model.py:512-657); dst and src rows must be
+ * disjoint sets (dead vs alive primitives, or freshly appended rows).  counts: [N] int32 scratch.            */
+int ubs_mcmc_relocate(int64_t N, int D, float *records, float *exp_avg, float *exp_avg_sq, int64_t K,
+                      const int64_t *dst_idx, const int64_t *src_idx, int32_t *counts, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,73 @@
+"""CPU tests of the train-step oracle (oracle/train_oracle.py): the restated loss against the fixture generated from
+the reference's own utils/loss_utils.py (tests/golden/make_golden_loss.py), Adam group layout, relocation algebra."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_ssim.npz")
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_loss_oracle_matches_reference_fixture(tag):
+    from oracle import train_oracle as T
+
+    z = np.load(GOLD)
+    img = torch.from_numpy(z[f"{tag}_img"]).requires_grad_(True)
+    gt = torch.from_numpy(z[f"{tag}_gt"])
+    assert abs(T.l1_loss(img, gt).item() - float(z[f"{tag}_l1"])) < 1e-7
+    assert abs(T.ssim(img[None], gt[None]).item() - float(z[f"{tag}_ssim"])) < 1e-6
+    loss = T.photometric_loss(img, gt, 0.2)
+    assert abs(loss.item() - float(z[f"{tag}_loss"])) < 1e-6
+    loss.backward()
+    ref = torch.from_numpy(z[f"{tag}_grad"])
+    assert (img.grad - ref).abs().max().item() <= 1e-6 * ref.abs().max().item() + 1e-10
+
+
+def test_relocate_oracle_properties():
+    from oracle import train_oracle as T
+
+    torch.manual_seed(0)
+    N, D = 50, 6
+    params = [torch.randn(N, w) for w in (3, 3, 3, 1, 4, 6, 15)]
+    before = [p.clone() for p in params]
+    dead = torch.tensor([3, 7, 11, 20])
+    src = torch.tensor([5, 5, 9, 5])
+    moments = [(torch.ones_like(p), torch.ones_like(p)) for p in params]
+    T.relocate(params, moments, dead, src)
+    # dead rows are copies of their sources except for the opacity
+    for k in (0, 1, 2, 4, 5, 6):
+        assert torch.equal(params[k][dead], before[k][src])
+    o = torch.sigmoid(before[3][5, 0])
+    want = (1 - (1 - o) ** (1.0 / 4.0)).clamp(0.005, 1 - torch.finfo(torch.float32).eps)
+    got = torch.sigmoid(params[3][torch.tensor([3, 7, 20, 5]), 0])
+    assert torch.allclose(got, want.expand(4), atol=1e-6)
+    assert moments[0][0][5].abs().sum() == 0 and moments[0][0][9].abs().sum() == 0
+    assert moments[0][0][3].abs().sum() > 0  # moments of the relocated (dead) rows are NOT reset by the reference
+    grown, gm = T.add_new(params, moments, torch.tensor([1, 1, 2]))
+    assert grown[0].shape[0] == N + 3 and gm[0][0].shape[0] == N + 3
+    assert torch.equal(grown[0][N:], params[0][torch.tensor([1, 1, 2])])
+    assert gm[3][0][N:].abs().sum() == 0 and gm[3][0][1].abs().sum() == 0
+
+
+def test_expon_lr_matches_reference_formula():
+    from ubs_b200.training import expon_lr
+
+    # utils/general_utils.py:52-65 evaluated by hand
+    for step in (0, 1, 100, 15000, 30000, 40000):
+        t = min(max(step / 30000, 0), 1)
+        want = np.exp(np.log(1.6e-4) * (1 - t) + np.log(1.6e-6) * t)
+        assert abs(expon_lr(step, 1.6e-4, 1.6e-6, lr_delay_mult=0.01, max_steps=30000) - want) < 1e-18
+    assert expon_lr(-1, 1.0, 1.0) == 0.0
+
+
+def test_packed_adam_lr_columns_follow_record_layout():
+    from ubs_b200 import fused
+    from ubs_b200.training import DEFAULT_LR
+
+    for D in (6, 7):
+        sl = fused.record_slices(D)
+        assert sl["opacity"].start == D + 3 and sl["scale"].start == 2 * D + 2  # the columns csrc/optim.cu assumes
+        assert sl["l_triangle"].stop <= fused.record_stride(D)
+    assert set(DEFAULT_LR) == set(sl)

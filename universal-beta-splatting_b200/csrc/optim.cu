@@ -1,0 +1,172 @@
+// The step after the backward pass, on the packed [N, stride] buffers:
+//   * ubs_adam_step: torch.optim.Adam(eps=1e-15) of scene/beta_model.py:239-268 -- seven parameter groups, one
+//     learning rate each -- as ONE bandwidth-bound pass over params / grads / exp_avg / exp_avg_sq with a learning
+//     rate per record column (read 4, write 3 record-sized streams).  The opacity and scale regularisers of
+//     train.py:122-124 are added to the gradient inside the same pass.
+//   * ubs_mcmc_relocate: the deterministic part of relocate_gs / add_new_gs (scene/beta_model.py:548-657): copy the
+//     sampled source rows into the destination rows with the opacity rescaled by the sampling multiplicity
+//     (_update_params, :548-565), write the new opacity back to the sources and reset their Adam moments
+//     (replace_tensors_to_optimizer(inds=...), :512-546).  The sampling itself (torch.multinomial) stays with the
+//     caller: it is defined by torch's RNG stream.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ubs {
+namespace {
+
+constexpr int kMaxStride = 64;
+
+struct AdamCols {
+    float step_size[kMaxStride];  // lr[col] / (1 - beta1^t); 0 for padding columns
+};
+
+// the library is compiled with --use_fast_math (expf -> ex2.approx); the regulariser touches one column per row, so
+// its sigmoid is evaluated in FP64 and rounded once
+__device__ __forceinline__ float precise_sigmoid(float x) { return (float)(1.0 / (1.0 + exp(-(double)x))); }
+
+__global__ void __launch_bounds__(256)
+adam_kernel(int64_t n_vec, int vec_per_row, float4 *__restrict__ params, const float4 *__restrict__ grads,
+            float4 *__restrict__ exp_avg, float4 *__restrict__ exp_avg_sq, AdamCols cols, float w1, float beta2,
+            float w2, float bc2_sqrt, float eps, int col_opacity, int col_scale, int D,
+            float reg_opacity, float reg_scale) {
+    __shared__ float s_step[kMaxStride];
+    if (threadIdx.x < kMaxStride) s_step[threadIdx.x] = cols.step_size[threadIdx.x];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / vec_per_row;
+        const int c0 = (int)(i - row * vec_per_row) * 4;
+        float4 p4 = params[i], g4 = __ldcs(grads + i), m4 = exp_avg[i], v4 = exp_avg_sq[i];
+        float p[4] = {p4.x, p4.y, p4.z, p4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+        float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + k;
+            if (reg_opacity != 0.f && c == col_opacity) {
+                // d/d raw of reg * mean(|sigmoid(raw)|): sigmoid > 0, so the |.| passes the derivative through
+                const float sg = precise_sigmoid(p[k]);
+                g[k] += reg_opacity * sg * (1.f - sg);
+            }
+            if (reg_scale != 0.f && row < 3 && c >= col_scale && c < col_scale + D) {
+                // train.py:124 regularises get_scale[:3] -- the first three PRIMITIVES, all D scales (reproduced);
+                // d softplus(raw) / d raw = sigmoid(raw)
+                g[k] += reg_scale * precise_sigmoid(p[k]);
+            }
+            m[k] = fmaf(w1, g[k] - m[k], m[k]);         // exp_avg.lerp_(grad, 1 - beta1)
+            v[k] = fmaf(w2 * g[k], g[k], v[k] * beta2);  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+            const float denom = __fdiv_rn(__fsqrt_rn(v[k]), bc2_sqrt) + eps;
+            p[k] = fmaf(-s_step[c], __fdiv_rn(m[k], denom), p[k]);  // param.addcdiv_(exp_avg, denom, value=-step_size)
+        }
+        params[i] = make_float4(p[0], p[1], p[2], p[3]);
+        exp_avg[i] = make_float4(m[0], m[1], m[2], m[3]);
+        exp_avg_sq[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__global__ void count_sources_kernel(int64_t K, const int64_t *__restrict__ src, int32_t *__restrict__ counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) atomicAdd(counts + src[i], 1);
+}
+
+// one warp per relocated row: copies the source record and rescales the opacity
+__global__ void __launch_bounds__(256)
+relocate_copy_kernel(int64_t K, int stride, int col_opacity, float *__restrict__ records,
+                     const int64_t *__restrict__ dst, const int64_t *__restrict__ src,
+                     const int32_t *__restrict__ counts) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= K) return;
+    const int64_t s = src[i], d = dst[i];
+    const float *in = records + s * stride;
+    float *out = records + d * stride;
+    for (int c = lane; c < stride; c += 32) {
+        float val = in[c];
+        if (c == col_opacity) {
+            // new = 1 - (1 - sigmoid(raw))^(1 / (ratio + 1)), clamped to [0.005, 1 - eps], stored as a logit
+            // (scene/beta_model.py:548-558); evaluated in FP64 and rounded once
+            const double op = (double)(1.f / (1.f + (float)exp(-(double)val)));
+            const float expo = 1.0f / (float)(counts[s] + 1);
+            float nw = 1.0f - (float)pow((double)(1.0f - (float)op), (double)expo);
+            nw = fminf(fmaxf(nw, 0.005f), 1.0f - 1.1920928955078125e-07f);
+            val = (float)log((double)nw / (double)(1.0f - nw));
+        }
+        out[c] = val;
+    }
+}
+
+// after every copy has been made: sources take the rescaled opacity of (any of) their copies -- all copies of one
+// source carry the same value -- and lose their Adam moments
+__global__ void __launch_bounds__(256)
+relocate_fixup_kernel(int64_t K, int stride, int col_opacity, float *__restrict__ records,
+                      float *__restrict__ exp_avg, float *__restrict__ exp_avg_sq, const int64_t *__restrict__ dst,
+                      const int64_t *__restrict__ src) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= K) return;
+    const int64_t s = src[i], d = dst[i];
+    if (lane == 0) records[s * stride + col_opacity] = records[d * stride + col_opacity];
+    if (exp_avg != nullptr)
+        for (int c = lane; c < stride; c += 32) {
+            exp_avg[s * stride + c] = 0.f;
+            exp_avg_sq[s * stride + c] = 0.f;
+        }
+}
+
+}  // namespace
+}  // namespace ubs
+
+extern "C" int ubs_adam_step(int64_t N, int D, float *records, const float *grads, float *exp_avg, float *exp_avg_sq,
+                             const double *h_lr, double beta1, double beta2, double eps, int64_t step,
+                             double opacity_reg, double scale_reg, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(N >= 0 && D >= 4 && D <= 8, "adam_step: bad sizes (N=%lld, D=%d)", (long long)N, D);
+    if (N == 0) return UBS_OK;
+    UBS_CHECK_ARG(records && grads && exp_avg && exp_avg_sq && h_lr, "adam_step: null pointer");
+    UBS_CHECK_ARG(step >= 1, "adam_step: step counts from 1 (got %lld)", (long long)step);
+    const int stride = UBS_RECORD_STRIDE(D);
+    UBS_CHECK_ARG(stride <= kMaxStride, "adam_step: stride %d exceeds %d", stride, kMaxStride);
+    // torch/optim/adam.py (_single_tensor_adam): python-double scalars, rounded to FP32 where they meet a tensor
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    AdamCols cols;
+    for (int c = 0; c < kMaxStride; ++c) cols.step_size[c] = c < stride ? (float)(h_lr[c] / bc1) : 0.f;
+    const int n_floats = UBS_RECORD_FLOATS(D);
+    for (int c = n_floats; c < stride; ++c) cols.step_size[c] = 0.f;  // padding columns never move
+    const int col_opacity = D + 3, col_scale = 2 * D + 2;
+    const float reg_o = (float)(opacity_reg / (double)N);            // mean over [N,1]
+    const float reg_s = (float)(scale_reg / (double)((N < 3 ? N : 3) * D));  // mean over get_scale[:3] = [3,D]
+    const int64_t n_vec = N * (stride / 4);
+    int sm = 148;
+    {
+        int dev = 0;
+        UBS_CUDA_TRY(cudaGetDevice(&dev));
+        UBS_CUDA_TRY(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int64_t blocks = ceil_div(n_vec, 256);
+    const unsigned grid = (unsigned)(blocks < (int64_t)sm * 16 ? blocks : (int64_t)sm * 16);
+    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        n_vec, stride / 4, (float4 *)records, (const float4 *)grads, (float4 *)exp_avg, (float4 *)exp_avg_sq, cols,
+        (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps, col_opacity,
+        col_scale, D, reg_o, reg_s);
+    UBS_LAUNCH_CHECK("adam_kernel");
+    return UBS_OK;
+}
+
+extern "C" int ubs_mcmc_relocate(int64_t N, int D, float *records, float *exp_avg, float *exp_avg_sq, int64_t K,
+                                 const int64_t *dst_idx, const int64_t *src_idx, int32_t *counts, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(N >= 0 && K >= 0 && D >= 4 && D <= 8, "mcmc_relocate: bad sizes");
+    if (K == 0 || N == 0) return UBS_OK;
+    UBS_CHECK_ARG(records && dst_idx && src_idx && counts, "mcmc_relocate: null pointer");
+    UBS_CHECK_ARG((exp_avg == nullptr) == (exp_avg_sq == nullptr), "mcmc_relocate: give both moment buffers or none");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int stride = UBS_RECORD_STRIDE(D), col_opacity = D + 3;
+    UBS_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)N * sizeof(int32_t), s));
+    count_sources_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, s>>>(K, src_idx, counts);
+    UBS_LAUNCH_CHECK("count_sources_kernel");
+    const unsigned grid = (unsigned)ceil_div(K * 32, 256);
+    relocate_copy_kernel<<<grid, 256, 0, s>>>(K, stride, col_opacity, records, dst_idx, src_idx, counts);
+    UBS_LAUNCH_CHECK("relocate_copy_kernel");
+    relocate_fixup_kernel<<<grid, 256, 0, s>>>(K, stride, col_opacity, records, exp_avg, exp_avg_sq, dst_idx, src_idx);
+    UBS_LAUNCH_CHECK("relocate_fixup_kernel");
+    return UBS_OK;
+}

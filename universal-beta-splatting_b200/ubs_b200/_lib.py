@@ -5,7 +5,7 @@ Replaces the reference's JIT/pybind backend loader (submodules/gsplat/cuda/_back
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libubs_b200.so")
@@ -47,6 +47,12 @@ SIGNATURES = {
                                       c_float, c_float, c_int, c_int, c_int, c_int] + [_P] * 11 + [c_size_t, _P]),
     "ubs_fused_project_bwd": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_int] +
                               [_P] * 10),
+    "ubs_l1_ssim_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "ubs_l1_ssim_loss": (c_int, [c_int, c_int, c_int, c_int, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64,
+                                 c_int64, c_int64, c_int64, c_float, c_float, _P, _P, _P, c_size_t, _P]),
+    "ubs_adam_step": (c_int, [c_int64, c_int, _P, _P, _P, _P, _P, c_double, c_double, c_double, c_int64, c_double,
+                              c_double, _P]),
+    "ubs_mcmc_relocate": (c_int, [c_int64, c_int, _P, _P, _P, c_int64, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -1,0 +1,247 @@
+"""The train step around the render, on the packed records.
+
+    render (fused.FusedRasterizer) -> l1_ssim_loss -> backward -> [NCCL all-reduce] -> PackedAdam.step
+
+mirrors one iteration of train.py:100-171 of the reference: `l1_loss` + `fused_ssim` (train.py:118-121), the
+opacity / scale regularisers (:122-124), `total_loss.backward()` (:128), `optimizer.step()` over the seven Adam
+groups of scene/beta_model.py:239-268 (:169) and the deterministic part of the MCMC relocation (:150-152).
+Every arithmetic step is a kernel of libubs_b200.so; there is no torch fallback.
+"""
+import ctypes
+import math
+from typing import Dict, Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import check, ptr
+from .fused import FusedRasterizer, record_slices, record_stride
+
+# learning rates of arguments/__init__.py:84-93 (position_lr_init is scaled by the scene extent by the caller)
+DEFAULT_LR = {"xyz": 0.00016, "mean": 0.001, "rgb": 0.001, "opacity": 0.05, "beta": 0.001, "scale": 0.005,
+              "l_triangle": 0.001}
+
+
+def expon_lr(step: int, lr_init: float, lr_final: float, lr_delay_steps: int = 0, lr_delay_mult: float = 1.0,
+             max_steps: int = 1000000) -> float:
+    """Log-linear learning-rate decay (utils/general_utils.py:34-67, used for the xyz group only)."""
+    if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+        return 0.0
+    delay = 1.0
+    if lr_delay_steps > 0:
+        delay = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0), 1))
+    t = min(max(step / max_steps, 0), 1)
+    return delay * math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+
+
+def _strides4(t: Tensor, layout: str):
+    """(sn, sc, sy, sx) element strides of a 4-D image tensor given as 'NHWC' or 'NCHW'."""
+    assert t.dim() == 4 and t.dtype == torch.float32 and t.is_cuda
+    s = t.stride()
+    if layout == "NHWC":
+        return s[0], s[3], s[1], s[2]
+    if layout == "NCHW":
+        return s[0], s[1], s[2], s[3]
+    raise ValueError(layout)
+
+
+class _LossWorkspace:
+    """Per-shape scratch of the loss kernels, cached on the device."""
+
+    _cache: Dict[tuple, Tensor] = {}
+
+    @classmethod
+    def get(cls, lib, C, ch, H, W, device) -> Tensor:
+        key = (C, ch, H, W, str(device))
+        ws = cls._cache.get(key)
+        if ws is None:
+            n = lib.ubs_l1_ssim_workspace_bytes(C, ch, H, W)
+            ws = torch.empty((n,), dtype=torch.uint8, device=device)
+            cls._cache[key] = ws
+        return ws
+
+
+@torch.no_grad()
+def l1_ssim_loss_fwd_bwd(img: Tensor, gt: Tensor, lambda_dssim: float = 0.2, grad_scale: float = 1.0,
+                         img_layout: str = "NHWC", gt_layout: str = "NCHW", want_grad: bool = True,
+                         v_img: Optional[Tensor] = None, loss_out: Optional[Tensor] = None):
+    """Loss values and (optionally) the image gradient in one call.
+
+    img: rendered image(s), [C,H,W,ch] ('NHWC', what the rasteriser writes) or [C,ch,H,W]; gt likewise.
+    Returns (loss_out [3] = (L1, SSIM, loss) on the device, v_img with img's shape and strides or None);
+    v_img = d(grad_scale * loss) / d img."""
+    lib = _lib.load()
+    isn, isc, isy, isx = _strides4(img, img_layout)
+    gsn, gsc, gsy, gsx = _strides4(gt, gt_layout)
+    if img_layout == "NHWC":
+        C, H, W, ch = img.shape
+    else:
+        C, ch, H, W = img.shape
+    g_shape = (gt.shape[0], gt.shape[3], gt.shape[1], gt.shape[2]) if gt_layout == "NHWC" else tuple(gt.shape)
+    assert g_shape == (C, ch, H, W), "img and gt disagree: %s vs %s" % (tuple(img.shape), tuple(gt.shape))
+    ws = _LossWorkspace.get(lib, C, ch, H, W, img.device)
+    if loss_out is None:
+        loss_out = torch.empty((3,), dtype=torch.float32, device=img.device)
+    if want_grad and v_img is None:
+        v_img = torch.empty_strided(img.shape, img.stride(), dtype=torch.float32, device=img.device)
+    if v_img is not None:
+        assert v_img.shape == img.shape and v_img.stride() == img.stride()
+    check(lib.ubs_l1_ssim_loss(C, ch, H, W, ptr(img), isn, isc, isy, isx, ptr(gt), gsn, gsc, gsy, gsx,
+                               float(lambda_dssim), float(grad_scale), ptr(loss_out),
+                               ptr(v_img) if want_grad else None, ptr(ws), ws.numel(),
+                               torch.cuda.current_stream().cuda_stream), "ubs_l1_ssim_loss")
+    return loss_out, (v_img if want_grad else None)
+
+
+class _L1SSIM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, gt, lambda_dssim, img_layout, gt_layout):
+        loss_out, v_img = l1_ssim_loss_fwd_bwd(img.detach(), gt, lambda_dssim, 1.0, img_layout, gt_layout,
+                                               want_grad=img.requires_grad)
+        ctx.save_for_backward(v_img)
+        return loss_out[2].clone()
+
+    @staticmethod
+    def backward(ctx, v_loss):
+        (v_img,) = ctx.saved_tensors
+        return (None if v_img is None else v_img * v_loss), None, None, None, None
+
+
+def l1_ssim_loss(img: Tensor, gt: Tensor, lambda_dssim: float = 0.2, img_layout: str = "NCHW",
+                 gt_layout: str = "NCHW") -> Tensor:
+    """Differentiable scalar (1 - lambda) * l1_loss(img, gt) + lambda * (1 - ssim(img, gt)), the expression of
+    train.py:118-121, for [C,ch,H,W] (default, the reference's image layout; a [ch,H,W] image is unsqueezed) or
+    [C,H,W,ch] tensors.  Gradient flows to `img` only."""
+    if img.dim() == 3:
+        img, gt = img.unsqueeze(0), gt.unsqueeze(0)
+    return _L1SSIM.apply(img, gt, lambda_dssim, img_layout, gt_layout)
+
+
+class PackedAdam:
+    """torch.optim.Adam(lr per group, betas=(0.9, 0.999), eps=1e-15) over the packed record buffer.
+
+    State: exp_avg / exp_avg_sq [N, stride] and the step count, as torch keeps them per parameter
+    (scene/beta_model.py:239-268).  `lr` maps the reference's group names to learning rates; `set_lr("xyz", ...)`
+    is what `update_learning_rate` (beta_model.py:278-284) does every iteration."""
+
+    GROUPS = ("xyz", "mean", "rgb", "opacity", "beta", "scale", "l_triangle")
+
+    def __init__(self, D: int, N: int, lr: Optional[Dict[str, float]] = None, betas=(0.9, 0.999), eps: float = 1e-15,
+                 device="cuda"):
+        self.lib = _lib.load()
+        self.D, self.N = D, N
+        self.stride = record_stride(D)
+        self.lr = dict(DEFAULT_LR if lr is None else lr)
+        assert set(self.lr) == set(self.GROUPS), "one learning rate per parameter group: %s" % (self.GROUPS,)
+        self.betas, self.eps = betas, eps
+        self.step_count = 0
+        self.exp_avg = torch.zeros((N, self.stride), dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros((N, self.stride), dtype=torch.float32, device=device)
+
+    def set_lr(self, group: str, value: float):
+        assert group in self.lr
+        self.lr[group] = float(value)
+
+    def lr_columns(self):
+        cols = [0.0] * self.stride
+        for name, sl in record_slices(self.D).items():
+            for c in range(sl.start, sl.stop):
+                cols[c] = self.lr[name]
+        return cols
+
+    @torch.no_grad()
+    def step(self, records: Tensor, grads: Tensor, opacity_reg: float = 0.0, scale_reg: float = 0.0):
+        """In-place update of `records` (and the moments) from `grads` ([N, stride], e.g. FusedRasterizer.backward's
+        output).  opacity_reg / scale_reg: coefficients of the regularisers of train.py:122-124 (0 = off)."""
+        N = records.shape[0]
+        assert records.shape == (N, self.stride) and grads.shape == records.shape == self.exp_avg.shape
+        assert records.is_cuda and records.is_contiguous() and grads.is_contiguous()
+        self.step_count += 1
+        cols = (ctypes.c_double * self.stride)(*self.lr_columns())
+        check(self.lib.ubs_adam_step(N, self.D, ptr(records), ptr(grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                     ctypes.cast(cols, ctypes.c_void_p), self.betas[0], self.betas[1], self.eps,
+                                     self.step_count, float(opacity_reg), float(scale_reg),
+                                     torch.cuda.current_stream().cuda_stream), "ubs_adam_step")
+
+    def grow(self, n_new: int):
+        """Zero moments for `n_new` appended rows (cat_tensors_to_optimizer, beta_model.py:446-474)."""
+        z = torch.zeros((n_new, self.stride), dtype=torch.float32, device=self.exp_avg.device)
+        self.exp_avg = torch.cat((self.exp_avg, z))
+        self.exp_avg_sq = torch.cat((self.exp_avg_sq, z))
+        self.N += n_new
+
+
+@torch.no_grad()
+def mcmc_relocate(records: Tensor, D: int, dst_idx: Tensor, src_idx: Tensor, adam: Optional[PackedAdam] = None):
+    """Rows dst_idx <- rows src_idx with the multiplicity-rescaled opacity; sources take the same opacity and lose
+    their Adam moments.  With dst = dead primitives and src = torch.multinomial samples of the alive ones this is
+    relocate_gs (scene/beta_model.py:575-620)."""
+    lib = _lib.load()
+    N, K = records.shape[0], dst_idx.numel()
+    assert src_idx.numel() == K and dst_idx.dtype == torch.int64 and src_idx.dtype == torch.int64
+    if K == 0:
+        return
+    counts = torch.empty((N,), dtype=torch.int32, device=records.device)
+    check(lib.ubs_mcmc_relocate(N, D, ptr(records), ptr(adam.exp_avg) if adam else None,
+                                ptr(adam.exp_avg_sq) if adam else None, K, ptr(dst_idx.contiguous()),
+                                ptr(src_idx.contiguous()), ptr(counts), torch.cuda.current_stream().cuda_stream),
+          "ubs_mcmc_relocate")
+
+
+@torch.no_grad()
+def mcmc_add(records: Tensor, D: int, src_idx: Tensor, adam: Optional[PackedAdam] = None) -> Tensor:
+    """add_new_gs (scene/beta_model.py:622-657) given the sampled sources: returns the grown record buffer whose
+    appended rows are the rescaled copies; the moments grow with zeros."""
+    K = src_idx.numel()
+    if K == 0:
+        return records
+    N = records.shape[0]
+    grown = torch.cat((records, torch.empty((K, records.shape[1]), dtype=records.dtype, device=records.device)))
+    if adam is not None:
+        adam.grow(K)
+    dst = torch.arange(N, N + K, dtype=torch.int64, device=records.device)
+    mcmc_relocate(grown, D, dst, src_idx, adam)
+    return grown
+
+
+def sample_alive(probs: Tensor, num: int, alive_indices: Optional[Tensor] = None, generator=None) -> Tensor:
+    """_sample_alives (scene/beta_model.py:567-573) without the bincount: the multinomial draw itself is torch's
+    (its result is defined by torch's RNG stream)."""
+    probs = probs / (probs.sum() + torch.finfo(torch.float32).eps)
+    idx = torch.multinomial(probs, num, replacement=True, generator=generator)
+    return idx if alive_indices is None else alive_indices[idx]
+
+
+class TrainStep:
+    """One full training iteration of one view per GPU on resident buffers:
+    forward -> L1+SSIM loss and its image gradient -> backward -> (all-reduce) -> Adam.  Zero host syncs."""
+
+    def __init__(self, rz: FusedRasterizer, adam: PackedAdam, lambda_dssim: float = 0.2, world: int = 1, group=None):
+        assert rz.C == 1
+        self.rz, self.adam, self.lam, self.world, self.group = rz, adam, lambda_dssim, world, group
+        dev = rz.device
+        self.v_rc = torch.empty_like(rz.render_colors)
+        self.v_ra = torch.zeros_like(rz.render_alphas)  # the loss does not depend on alpha
+        self.loss_out = torch.empty((3,), dtype=torch.float32, device=dev)
+        self.v_records = None
+
+    @torch.no_grad()
+    def step(self, records: Tensor, viewmats, Ks, cam_pos, timestamps, backgrounds, gt: Tensor, gt_layout="NCHW",
+             opacity_reg: float = 0.0, scale_reg: float = 0.0, batch_size: int = 1) -> Tensor:
+        from . import parallel
+
+        rz = self.rz
+        if self.v_records is None or self.v_records.shape != records.shape:
+            self.v_records = torch.empty_like(records)
+        rc, _ = rz.forward(records, viewmats, Ks, cam_pos, timestamps, backgrounds)
+        if gt.dim() == 3:
+            gt = gt.unsqueeze(0)
+        with rz._stage("l1_ssim_loss"):
+            l1_ssim_loss_fwd_bwd(rc, gt, self.lam, 1.0 / batch_size, "NHWC", gt_layout, True, self.v_rc, self.loss_out)
+        rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, self.v_rc, self.v_ra, self.v_records)
+        with rz._stage("allreduce"):
+            parallel.allreduce_gradients(self.v_records, self.world, None, self.group)
+        with rz._stage("adam_step"):
+            self.adam.step(records, self.v_records, opacity_reg, scale_reg)
+        return self.loss_out
