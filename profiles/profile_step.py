@@ -10,10 +10,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "universal-beta-splatting_b200"))
-from ubs_b200 import fused, synth  # noqa: E402
+from ubs_b200 import fused, synth, training  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+full = len(sys.argv) > 3 and sys.argv[3] == "full"  # full train step: + L1/SSIM loss + Adam
 scene, cams, bg, cfg = synth.make_config(name, device="cuda", cams_override=8)
 rec = fused.pack_records(scene.D, *scene.tensors())
 W, H = cfg["width"], cfg["height"]
@@ -22,10 +23,16 @@ v_rc = torch.randn(1, H, W, 3, device="cuda") / (W * H)
 v_ra = torch.zeros(1, H, W, 1, device="cuda")
 vrec = torch.empty_like(rec)
 bgd = bg[None]
+if full:
+    tstep = training.TrainStep(rz, training.PackedAdam(scene.D, scene.N))
+    gt = torch.rand(1, 3, H, W, device="cuda")
 for k in range(iters):
     cam = cams[k % len(cams)]
     ts = torch.tensor([cam.timestamp], device="cuda") if scene.D == 7 else None
     args = (rec, cam.viewmat[None], cam.K[None], cam.cam_pos[None], ts, bgd)
+    if full:
+        tstep.step(*args, gt, opacity_reg=0.01, scale_reg=0.01)
+        continue
     rz.forward(*args)
     rz.backward(*args, v_rc, v_ra, vrec)
 torch.cuda.synchronize()
