@@ -413,6 +413,9 @@ def run_ours(args, rank, local_rank, world):
     stage_roof["rasterize_bwd"] = {"bound": "fp32", "ms": stages_train.get("rasterize_bwd", (0, float("nan")))[1],
                                    "slots": 9.0 * counts["E_cull"] + 45.0 * counts["E_acc"]}
     hbm_stage("adam_step", stages_full.get("adam_step", (0, float("nan")))[1], 7 * N * rec_b)
+    # projection backward with the Adam epilogue: read params + 2 moments, write them back, + the screen-space gradients
+    hbm_stage("fused_project_bwd_adam", stages_full.get("fused_project_bwd_adam", (0, float("nan")))[1],
+              6 * N * rec_b + vis * 76)
     # loss: read img + gt, write 3 maps (pass 1); read 3 maps + img + gt, write v_img (pass 2): 10 image-sized streams
     hbm_stage("l1_ssim_loss", stages_full.get("l1_ssim_loss", (0, float("nan")))[1], 10 * P * 3 * 4)
     rb = stage_roof["rasterize_bwd"]
@@ -451,7 +454,8 @@ def run_ours(args, rank, local_rank, world):
                        "ms_per_step": ms_full / args.steps,
                        "what": "forward + fused L1/SSIM loss and image gradient + backward" +
                                (" + NCCL allreduce" if world > 1 else "") +
-                               " + fused Adam over the packed records with the opacity/scale regularisers "
+                               " + Adam over the packed records with the opacity/scale regularisers (inside the "
+                               "projection-backward kernel at 1 GPU, a separate pass after the all-reduce otherwise) "
                                "(train.py:100-171 for one view per GPU)",
                        "gpu_launches": launches_full, "clocks": clocks_full,
                        "stages_ms": {k: v[1] for k, v in stages_full.items()}},

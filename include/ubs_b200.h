@@ -272,6 +272,17 @@ int ubs_adam_step(int64_t N, int D, float *records, const float *grads, float *e
                   const double *h_lr, double beta1, double beta2, double eps, int64_t step, double opacity_reg,
                   double scale_reg, void *stream);
 
+/* ubs_fused_project_bwd + ubs_adam_step in one launch, for single-GPU batch-1 training (the reference's default,
+ * arguments/__init__.py:103): the gradient records never touch HBM; `records`, `exp_avg`, `exp_avg_sq` are updated
+ * in place.  Same arguments as the two calls it replaces (no v_records).                                      */
+int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *records, const float *viewmats, const float *Ks,
+                               const float *cam_pos, const float *timestamps, int width, int height, float eps2d,
+                               int calc_compensations, const int32_t *radii, const float *conics,
+                               const float *v_means2d, const float *v_depths, const float *v_conics,
+                               const float *v_opacities, const float *v_betas, const float *v_colors, float *exp_avg,
+                               float *exp_avg_sq, const double *h_lr, double beta1, double beta2, double eps,
+                               int64_t step, double opacity_reg, double scale_reg, void *stream);
+
 /* MCMC relocation given the sampled indices: rows dst_idx[i] <- rows src_idx[i] with the opacity rescaled to
  * 1 - (1 - o)^(1/(m+1)), m = multiplicity of the source among src_idx, clamped to [0.005, 1 - eps]; the sources
  * take the same opacity and their Adam moments are zeroed (exp_avg / exp_avg_sq may both be NULL).

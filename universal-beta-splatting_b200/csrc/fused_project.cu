@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "cond_math.cuh"
 #include "isect.cuh"
+#include "optim.cuh"
 #include "proj_math.cuh"
 
 namespace ubs {
@@ -207,31 +208,60 @@ __device__ __forceinline__ void tma_bulk_s2g(void *dst_gmem, const void *src_sme
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+__device__ __forceinline__ void tma_bulk_s2g_issue(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // Backward of fused_project_fwd_kernel: one thread per primitive, looping over cameras, so the per-primitive sums
 // need no atomics.  Recomputes the cheap forward intermediates from the record instead of storing them.
-template <int D, int MINB>
+//
+// ADAM = true (single-GPU, batch-1 training: nothing has to be summed over ranks or views first): the Adam moment
+// tiles of the CTA's records are fetched with two more bulk copies at kernel start, so they land during the long
+// gradient computation; every thread then applies torch.optim.Adam to its own row straight from the gradient in
+// its registers and the updated parameters and moments go back with three bulk stores.  The gradient records are
+// never written: 6 record-sized HBM streams instead of the 2 + 7 of backward-then-optimiser.
+template <int D, int MINB, bool ADAM>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
-fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records, const float *__restrict__ viewmats,
+fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in, const float *__restrict__ viewmats,
                          const float *__restrict__ Ks, const float *__restrict__ cam_pos,
                          const float *__restrict__ timestamps, uint32_t width, uint32_t height, float eps2d,
                          int calc_comp, const int32_t *__restrict__ radii, const float *__restrict__ conics,
                          const float *__restrict__ v_means2d, const float *__restrict__ v_depths,
                          const float *__restrict__ v_conics, const float *__restrict__ v_opacities,
                          const float *__restrict__ v_betas, const float *__restrict__ v_colors,
-                         float *__restrict__ v_records) {
+                         float *__restrict__ v_records, float *__restrict__ exp_avg,
+                         float *__restrict__ exp_avg_sq, const AdamParams adam) {
     constexpr int Cd = D - 3, M = NdDims<D>::M;
     constexpr int STRIDE = UBS_RECORD_STRIDE(D);
-    __shared__ __align__(128) float s_rec[kFusedThreads * STRIDE];
-    __shared__ __align__(8) uint64_t s_bar;
+    extern __shared__ __align__(128) float s_tiles[];  // [records][exp_avg][exp_avg_sq] (the last two with ADAM)
+    float *const s_rec = s_tiles;
+    float *const s_m = s_tiles + kFusedThreads * STRIDE;
+    float *const s_v = s_tiles + 2 * kFusedThreads * STRIDE;
+    __shared__ __align__(8) uint64_t s_bar, s_bar2;
+    const float *records = records_in;
 
     const int64_t base = (int64_t)blockIdx.x * kFusedThreads;
     const int n_here = (int)min((int64_t)kFusedThreads, N - base);
     const uint32_t bytes = (uint32_t)n_here * STRIDE * sizeof(float);
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        if constexpr (ADAM) mbar_init(&s_bar2, 1);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(&s_bar, bytes);
         tma_bulk_g2s(s_rec, records + base * STRIDE, bytes, &s_bar);
+        if constexpr (ADAM) {
+            mbar_expect_tx(&s_bar2, 2 * bytes);
+            tma_bulk_g2s(s_m, exp_avg + base * STRIDE, bytes, &s_bar2);
+            tma_bulk_g2s(s_v, exp_avg_sq + base * STRIDE, bytes, &s_bar2);
+        }
     }
 
     // Compaction: only primitives visible in some camera have a non-zero gradient.  Their row indices are packed to
@@ -239,7 +269,7 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records, co
     // the remaining warps go straight to the zero fill (about half the primitives of a frame are culled).
     __shared__ int s_row[kFusedThreads];
     __shared__ int s_wcnt[kFusedThreads / 32];
-    int my_row = -1;
+    int my_row = -1, any_row = -1;
     {
         bool vis = false;
         if (threadIdx.x < n_here) {
@@ -256,9 +286,13 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records, co
             if (w < (int)warp) before += c;
             n_vis += c;
         }
-        if (vis) s_row[before + __popc(m & ((1u << lane) - 1u))] = (int)threadIdx.x;
+        const int vis_before = before + __popc(m & ((1u << lane) - 1u));
+        if (vis) s_row[vis_before] = (int)threadIdx.x;
+        // with ADAM the culled rows are listed behind the visible ones: every row is updated by exactly one thread
+        if (ADAM && !vis && (int)threadIdx.x < n_here) s_row[n_vis + ((int)threadIdx.x - vis_before)] = (int)threadIdx.x;
         __syncthreads();
         if ((int)threadIdx.x < n_vis) my_row = s_row[threadIdx.x];
+        if (ADAM && (int)threadIdx.x < n_here) any_row = s_row[threadIdx.x];
     }
     mbar_wait(&s_bar, 0);  // the records have landed (the visibility loads above overlapped the bulk copy)
     const int64_t gid = base + my_row;
@@ -414,6 +448,53 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records, co
         for (int k = 0; k < M; ++k) grad[3 * D + 2 + k] = vlt[k];
     }
 
+    if constexpr (ADAM) {
+        mbar_wait(&s_bar2, 0);  // the moment tiles landed long ago
+        if (any_row >= 0) {
+            const int64_t row = base + any_row;
+            float4 *p4 = reinterpret_cast<float4 *>(s_rec + any_row * STRIDE);
+            float4 *m4 = reinterpret_cast<float4 *>(s_m + any_row * STRIDE);
+            float4 *v4 = reinterpret_cast<float4 *>(s_v + any_row * STRIDE);
+            // regularisers (train.py:122-124): statically indexed columns, so the unrolled update below stays lean
+            if (adam.reg_opacity != 0.f) grad[D + 3] += adam_reg_grad(adam, row, D + 3, s_rec[any_row * STRIDE + D + 3]);
+            if (adam.reg_scale != 0.f && row < 3) {
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    grad[2 * D + 2 + k] += adam_reg_grad(adam, row, 2 * D + 2 + k, s_rec[any_row * STRIDE + 2 * D + 2 + k]);
+            }
+            // moments from the gradient in registers (unrolled, a few instructions per element) ...
+#pragma unroll
+            for (int k = 0; k < STRIDE / 4; ++k) {
+                float4 m = m4[k], v = v4[k];
+                adam_moments(adam, grad[4 * k + 0], m.x, v.x);
+                adam_moments(adam, grad[4 * k + 1], m.y, v.y);
+                adam_moments(adam, grad[4 * k + 2], m.z, v.z);
+                adam_moments(adam, grad[4 * k + 3], m.w, v.w);
+                m4[k] = m, v4[k] = v;
+            }
+            // ... then the parameter update as a rolled loop (IEEE sqrt and division: kept out of the unrolled code)
+#pragma unroll 1
+            for (int k = 0; k < STRIDE / 4; ++k) {
+                float4 p = p4[k];
+                const float4 m = m4[k], v = v4[k];
+                p.x = adam_apply(adam, adam.step_size[4 * k + 0], p.x, m.x, v.x);
+                p.y = adam_apply(adam, adam.step_size[4 * k + 1], p.y, m.y, v.y);
+                p.z = adam_apply(adam, adam.step_size[4 * k + 2], p.z, m.z, v.z);
+                p.w = adam_apply(adam, adam.step_size[4 * k + 3], p.w, m.w, v.w);
+                p4[k] = p;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tma_bulk_s2g_issue(const_cast<float *>(records_in) + base * STRIDE, s_rec, bytes);
+            tma_bulk_s2g_issue(exp_avg + base * STRIDE, s_m, bytes);
+            tma_bulk_s2g_issue(exp_avg_sq + base * STRIDE, s_v, bytes);
+            tma_bulk_commit_wait();
+        }
+        return;
+    }
+
     // ---- stage the gradient records in shared memory and write them with one TMA bulk store --------------------
     __syncthreads();  // all record reads done; reuse s_rec
     if ((int)threadIdx.x < n_here) {  // zero rows for the culled primitives (every row, then the live ones overwrite)
@@ -508,14 +589,64 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
     const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
     // compiled for 3 resident CTAs per SM (168 registers, ~0.6 KB of spills): measured 0.32 ms against 0.38 ms for the
     // spill-free 255-register build at 3M primitives -- the kernel is latency bound, occupancy wins
+    const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
+    const AdamParams unused{};
     if (D == 6)
-        fused_project_bwd_kernel<6, 3><<<gx, kFusedThreads, 0, s>>>(
+        fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
-            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records);
+            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records,
+            nullptr, nullptr, unused);
     else
-        fused_project_bwd_kernel<7, 3><<<gx, kFusedThreads, 0, s>>>(
+        fused_project_bwd_kernel<7, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
-            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records);
+            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records,
+            nullptr, nullptr, unused);
     UBS_LAUNCH_CHECK("fused_project_bwd_kernel");
+    return UBS_OK;
+}
+
+extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *records, const float *viewmats,
+                                          const float *Ks, const float *cam_pos, const float *timestamps, int width,
+                                          int height, float eps2d, int calc_compensations, const int32_t *radii,
+                                          const float *conics, const float *v_means2d, const float *v_depths,
+                                          const float *v_conics, const float *v_opacities, const float *v_betas,
+                                          const float *v_colors, float *exp_avg, float *exp_avg_sq, const double *h_lr,
+                                          double beta1, double beta2, double eps, int64_t step, double opacity_reg,
+                                          double scale_reg, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "fused_project_bwd_adam: bad sizes");
+    UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd_adam: D must be 6 or 7 (got %d)", D);
+    if (N == 0) return UBS_OK;
+    UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && conics && v_means2d && v_conics && v_opacities &&
+                      v_betas && exp_avg && exp_avg_sq && h_lr,
+                  "fused_project_bwd_adam: null pointer");
+    UBS_CHECK_ARG(D != 7 || timestamps != nullptr, "fused_project_bwd_adam: D=7 needs timestamps");
+    UBS_CHECK_ARG(step >= 1, "fused_project_bwd_adam: step counts from 1 (got %lld)", (long long)step);
+    UBS_CHECK_ARG((((uintptr_t)records | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
+                  "fused_project_bwd_adam: records / moments must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
+    const size_t smem = (size_t)3 * kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
+    const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
+    if (D == 6) {
+        UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<6, 3, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<6, 3, true>,
+                                          cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        fused_project_bwd_kernel<6, 3, true><<<gx, kFusedThreads, smem, s>>>(
+            C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
+            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
+            exp_avg, exp_avg_sq, a);
+    } else {
+        UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<7, 3, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<7, 3, true>,
+                                          cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        fused_project_bwd_kernel<7, 3, true><<<gx, kFusedThreads, smem, s>>>(
+            C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
+            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
+            exp_avg, exp_avg_sq, a);
+    }
+    UBS_LAUNCH_CHECK("fused_project_bwd_adam_kernel");
     return UBS_OK;
 }

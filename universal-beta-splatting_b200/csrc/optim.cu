@@ -11,27 +11,16 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "optim.cuh"
 
 namespace ubs {
 namespace {
 
-constexpr int kMaxStride = 64;
-
-struct AdamCols {
-    float step_size[kMaxStride];  // lr[col] / (1 - beta1^t); 0 for padding columns
-};
-
-// the library is compiled with --use_fast_math (expf -> ex2.approx); the regulariser touches one column per row, so
-// its sigmoid is evaluated in FP64 and rounded once
-__device__ __forceinline__ float precise_sigmoid(float x) { return (float)(1.0 / (1.0 + exp(-(double)x))); }
-
 __global__ void __launch_bounds__(256)
 adam_kernel(int64_t n_vec, int vec_per_row, float4 *__restrict__ params, const float4 *__restrict__ grads,
-            float4 *__restrict__ exp_avg, float4 *__restrict__ exp_avg_sq, AdamCols cols, float w1, float beta2,
-            float w2, float bc2_sqrt, float eps, int col_opacity, int col_scale, int D,
-            float reg_opacity, float reg_scale) {
-    __shared__ float s_step[kMaxStride];
-    if (threadIdx.x < kMaxStride) s_step[threadIdx.x] = cols.step_size[threadIdx.x];
+            float4 *__restrict__ exp_avg, float4 *__restrict__ exp_avg_sq, AdamParams a) {
+    __shared__ float s_step[kAdamMaxStride];
+    if (threadIdx.x < kAdamMaxStride) s_step[threadIdx.x] = a.step_size[threadIdx.x];
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = i / vec_per_row;
@@ -41,21 +30,8 @@ adam_kernel(int64_t n_vec, int vec_per_row, float4 *__restrict__ params, const f
         float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int c = c0 + k;
-            if (reg_opacity != 0.f && c == col_opacity) {
-                // d/d raw of reg * mean(|sigmoid(raw)|): sigmoid > 0, so the |.| passes the derivative through
-                const float sg = precise_sigmoid(p[k]);
-                g[k] += reg_opacity * sg * (1.f - sg);
-            }
-            if (reg_scale != 0.f && row < 3 && c >= col_scale && c < col_scale + D) {
-                // train.py:124 regularises get_scale[:3] -- the first three PRIMITIVES, all D scales (reproduced);
-                // d softplus(raw) / d raw = sigmoid(raw)
-                g[k] += reg_scale * precise_sigmoid(p[k]);
-            }
-            m[k] = fmaf(w1, g[k] - m[k], m[k]);         // exp_avg.lerp_(grad, 1 - beta1)
-            v[k] = fmaf(w2 * g[k], g[k], v[k] * beta2);  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-            const float denom = __fdiv_rn(__fsqrt_rn(v[k]), bc2_sqrt) + eps;
-            p[k] = fmaf(-s_step[c], __fdiv_rn(m[k], denom), p[k]);  // param.addcdiv_(exp_avg, denom, value=-step_size)
+            g[k] += adam_reg_grad(a, row, c0 + k, p[k]);
+            adam_update(a, s_step[c0 + k], p[k], g[k], m[k], v[k]);
         }
         params[i] = make_float4(p[0], p[1], p[2], p[3]);
         exp_avg[i] = make_float4(m[0], m[1], m[2], m[3]);
@@ -124,16 +100,8 @@ extern "C" int ubs_adam_step(int64_t N, int D, float *records, const float *grad
     UBS_CHECK_ARG(records && grads && exp_avg && exp_avg_sq && h_lr, "adam_step: null pointer");
     UBS_CHECK_ARG(step >= 1, "adam_step: step counts from 1 (got %lld)", (long long)step);
     const int stride = UBS_RECORD_STRIDE(D);
-    UBS_CHECK_ARG(stride <= kMaxStride, "adam_step: stride %d exceeds %d", stride, kMaxStride);
-    // torch/optim/adam.py (_single_tensor_adam): python-double scalars, rounded to FP32 where they meet a tensor
-    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
-    AdamCols cols;
-    for (int c = 0; c < kMaxStride; ++c) cols.step_size[c] = c < stride ? (float)(h_lr[c] / bc1) : 0.f;
-    const int n_floats = UBS_RECORD_FLOATS(D);
-    for (int c = n_floats; c < stride; ++c) cols.step_size[c] = 0.f;  // padding columns never move
-    const int col_opacity = D + 3, col_scale = 2 * D + 2;
-    const float reg_o = (float)(opacity_reg / (double)N);            // mean over [N,1]
-    const float reg_s = (float)(scale_reg / (double)((N < 3 ? N : 3) * D));  // mean over get_scale[:3] = [3,D]
+    UBS_CHECK_ARG(stride <= kAdamMaxStride, "adam_step: stride %d exceeds %d", stride, kAdamMaxStride);
+    const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
     const int64_t n_vec = N * (stride / 4);
     int sm = 148;
     {
@@ -143,10 +111,8 @@ extern "C" int ubs_adam_step(int64_t N, int D, float *records, const float *grad
     }
     const int64_t blocks = ceil_div(n_vec, 256);
     const unsigned grid = (unsigned)(blocks < (int64_t)sm * 16 ? blocks : (int64_t)sm * 16);
-    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        n_vec, stride / 4, (float4 *)records, (const float4 *)grads, (float4 *)exp_avg, (float4 *)exp_avg_sq, cols,
-        (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)sqrt(bc2), (float)eps, col_opacity,
-        col_scale, D, reg_o, reg_s);
+    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_vec, stride / 4, (float4 *)records, (const float4 *)grads,
+                                                        (float4 *)exp_avg, (float4 *)exp_avg_sq, a);
     UBS_LAUNCH_CHECK("adam_kernel");
     return UBS_OK;
 }

@@ -226,9 +226,12 @@ class FusedRasterizer:
     @torch.no_grad()
     def backward(self, records: Tensor, viewmats: Tensor, Ks: Tensor, cam_pos: Tensor, timestamps: Optional[Tensor],
                  backgrounds: Optional[Tensor], v_render_colors: Tensor, v_render_alphas: Tensor,
-                 v_records: Optional[Tensor] = None) -> Tensor:
+                 v_records: Optional[Tensor] = None, adam=None, opacity_reg: float = 0.0,
+                 scale_reg: float = 0.0) -> Optional[Tensor]:
         """Gradient of the most recent forward() w.r.t. the packed records ([N, stride], same layout).
-        Must be called before the next forward(): it reuses that frame's tile lists and screen-space records."""
+        Must be called before the next forward(): it reuses that frame's tile lists and screen-space records.
+        With `adam` (a training.PackedAdam) the optimiser step is applied inside the projection-backward kernel:
+        `records` and the moments are updated in place, no gradient buffer is produced and None is returned."""
         lib, s = self.lib, torch.cuda.current_stream().cuda_stream
         C, N, D = self.C, self.N, self.D
         self._grad_buffers().zero_()  # one memset for all five screen-space gradient arrays
@@ -242,6 +245,20 @@ class FusedRasterizer:
             ptr(self.offsets), ptr(self.flatten_ids), ptr(self.render_alphas), ptr(self.last_ids), ptr(v_rc),
             ptr(v_ra), ptr(self.v_means2d), ptr(self.v_conics), ptr(self.v_colors), ptr(self.v_opacities),
             ptr(self.v_betas), s), "ubs_rasterize_bwd")
+        if adam is not None:
+            # single-GPU batch-1 training: projection backward + Adam in one launch, records updated in place
+            import ctypes
+
+            adam.step_count += 1
+            cols = (ctypes.c_double * adam.stride)(*adam.lr_columns())
+            with self._stage("fused_project_bwd_adam"):
+              check(lib.ubs_fused_project_bwd_adam(
+                C, N, D, ptr(records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), self.W, self.H,
+                self.eps2d, 1 if self.aa else 0, ptr(self.radii), ptr(self.conics), ptr(self.v_means2d), None,
+                ptr(self.v_conics), ptr(self.v_opacities), ptr(self.v_betas), ptr(self.v_colors), ptr(adam.exp_avg),
+                ptr(adam.exp_avg_sq), ctypes.cast(cols, ctypes.c_void_p), adam.betas[0], adam.betas[1], adam.eps,
+                adam.step_count, float(opacity_reg), float(scale_reg), s), "ubs_fused_project_bwd_adam")
+            return None
         if v_records is None:
             v_records = torch.empty_like(records)
         with self._stage("fused_project_bwd"):

@@ -217,9 +217,13 @@ class TrainStep:
     """One full training iteration of one view per GPU on resident buffers:
     forward -> L1+SSIM loss and its image gradient -> backward -> (all-reduce) -> Adam.  Zero host syncs."""
 
-    def __init__(self, rz: FusedRasterizer, adam: PackedAdam, lambda_dssim: float = 0.2, world: int = 1, group=None):
+    def __init__(self, rz: FusedRasterizer, adam: PackedAdam, lambda_dssim: float = 0.2, world: int = 1, group=None,
+                 fuse_adam: bool = True):
         assert rz.C == 1
         self.rz, self.adam, self.lam, self.world, self.group = rz, adam, lambda_dssim, world, group
+        # one view per optimiser step on one GPU (the reference's default batch_size = 1): nothing to sum before the
+        # update, so Adam rides in the projection-backward kernel and the gradient records never reach HBM
+        self.fuse_adam = fuse_adam
         dev = rz.device
         self.v_rc = torch.empty_like(rz.render_colors)
         self.v_ra = torch.zeros_like(rz.render_alphas)  # the loss does not depend on alpha
@@ -232,13 +236,18 @@ class TrainStep:
         from . import parallel
 
         rz = self.rz
-        if self.v_records is None or self.v_records.shape != records.shape:
+        fused_update = self.fuse_adam and self.world == 1
+        if not fused_update and (self.v_records is None or self.v_records.shape != records.shape):
             self.v_records = torch.empty_like(records)
         rc, _ = rz.forward(records, viewmats, Ks, cam_pos, timestamps, backgrounds)
         if gt.dim() == 3:
             gt = gt.unsqueeze(0)
         with rz._stage("l1_ssim_loss"):
             l1_ssim_loss_fwd_bwd(rc, gt, self.lam, 1.0 / batch_size, "NHWC", gt_layout, True, self.v_rc, self.loss_out)
+        if fused_update:
+            rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, self.v_rc, self.v_ra, None, self.adam,
+                        opacity_reg, scale_reg)
+            return self.loss_out
         rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, self.v_rc, self.v_ra, self.v_records)
         with rz._stage("allreduce"):
             parallel.allreduce_gradients(self.v_records, self.world, None, self.group)
