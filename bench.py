@@ -393,11 +393,24 @@ def run_ours(args, rank, local_rank, world):
     passes = (key_bits + 7) // 8
     stage_roof = {}
 
+    stage_kernels = {  # stage -> the kernels it launches (keys of profiles/traffic.json)
+        "fused_project_fwd": ["fused_project_fwd_kernel"],
+        "isect_emit_sort_offsets": ["bin_scan_kernel", "bin_emit_kernel", "segment_sort_kernel",
+                                    "segment_sort_big_kernel"],
+        "fused_project_bwd": ["fused_project_bwd_kernel"], "adam_step": ["adam_kernel"],
+        "fused_project_bwd_adam": ["fused_project_bwd_adam_kernel"],
+        "l1_ssim_loss": ["ssim_fwd_kernel", "loss_finalize_kernel", "ssim_bwd_kernel"],
+    }
+
+    def stage_traffic(name):
+        ks = stage_kernels.get(name, [])
+        return sum(traffic[k] for k in ks) if ks and all(k in traffic for k in ks) else None
+
     def hbm_stage(name, ms, nbytes):
         if ms == ms and ms > 0:
             a = nbytes / (ms * 1e-3) / 1e9
             stage_roof[name] = {"bound": "hbm", "ms": ms, "algorithmic_bytes": nbytes, "achieved": a, "peak": hbm_peak,
-                                "unit": "GB/s", "frac": a / hbm_peak, "traffic": traffic.get(name)}
+                                "unit": "GB/s", "frac": a / hbm_peak, "traffic": stage_traffic(name)}
 
     hbm_stage("fused_project_fwd", stages.get("fused_project_fwd", (0, float("nan")))[1], N * rec_b + vis * 36)
     # SURVEY 8(d) unit figure: emit 12 B/pair + onesweep I (8 + 24 p) + offsets 8 B/pair.  The tile-binning route
@@ -411,7 +424,8 @@ def run_ours(args, rank, local_rank, world):
     hbm_stage("fused_project_bwd", stages_train.get("fused_project_bwd", (0, float("nan")))[1],
               2 * N * rec_b + vis * 76)
     stage_roof["rasterize_bwd"] = {"bound": "fp32", "ms": stages_train.get("rasterize_bwd", (0, float("nan")))[1],
-                                   "slots": 9.0 * counts["E_cull"] + 45.0 * counts["E_acc"]}
+                                   "slots": 9.0 * counts["E_cull"] + 45.0 * counts["E_acc"],
+                                   "traffic": traffic.get("rasterize_bwd3_kernel")}
     hbm_stage("adam_step", stages_full.get("adam_step", (0, float("nan")))[1], 7 * N * rec_b)
     # projection backward with the Adam epilogue: read params + 2 moments, write them back, + the screen-space gradients
     hbm_stage("fused_project_bwd_adam", stages_full.get("fused_project_bwd_adam", (0, float("nan")))[1],

@@ -14,7 +14,8 @@ from ubs_b200 import fused, synth, training  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-full = len(sys.argv) > 3 and sys.argv[3] == "full"  # full train step: + L1/SSIM loss + Adam
+full = len(sys.argv) > 3 and sys.argv[3].startswith("full")  # full train step: + L1/SSIM loss + Adam
+fuse = not (len(sys.argv) > 3 and sys.argv[3] == "full_unfused")  # Adam inside the projection backward (1 GPU) or separate
 scene, cams, bg, cfg = synth.make_config(name, device="cuda", cams_override=8)
 rec = fused.pack_records(scene.D, *scene.tensors())
 W, H = cfg["width"], cfg["height"]
@@ -24,7 +25,7 @@ v_ra = torch.zeros(1, H, W, 1, device="cuda")
 vrec = torch.empty_like(rec)
 bgd = bg[None]
 if full:
-    tstep = training.TrainStep(rz, training.PackedAdam(scene.D, scene.N))
+    tstep = training.TrainStep(rz, training.PackedAdam(scene.D, scene.N), fuse_adam=fuse)
     gt = torch.rand(1, 3, H, W, device="cuda")
 for k in range(iters):
     cam = cams[k % len(cams)]

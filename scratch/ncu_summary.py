@@ -35,6 +35,9 @@ for rep in sys.argv[1:]:
         def to_bytes(m):
             v, u = vals.get(m, (0.0, "byte"))
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-        traffic[short.split("<")[0]] = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+        key = short.split("<")[0]
+        if key == "fused_project_bwd_kernel" and short.rstrip().endswith(", 1>"):
+            key = "fused_project_bwd_adam_kernel"  # the ADAM = true instantiation
+        traffic[key] = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
         print()
 print("TRAFFIC", json.dumps(traffic))
