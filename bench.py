@@ -22,6 +22,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "universal-beta-splatting_b200"))
 sys.path.insert(0, ROOT)
 
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries the ONE JSON line
+# the gradient all-reduce is pipelined against the projection backward / Adam kernels (parallel.pipelined_backward);
+# NCCL's kernels only get SMs next to those full-machine grids from a high-priority stream (measured at 2 GPUs)
+os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
+
 import torch  # noqa: E402
 
 WORKLOADS = {

@@ -265,11 +265,12 @@ int ubs_l1_ssim_loss(int C, int channels, int height, int width, const float *im
 
 /* torch.optim.Adam(eps) over the packed records, one learning rate per record column (h_lr: HOST array of
  * UBS_RECORD_STRIDE(D) doubles; padding columns are never moved).  replaces optimizer.step() over the seven
- * parameter groups of scene/beta_model.py:239-268 (train.py:169).  `step` counts from 1.  opacity_reg / scale_reg
+ * parameter groups of scene/beta_model.py:239-268 (train.py:169).  `step` counts from 1.  All four buffers are the
+ * full [N, stride] arrays; a row range lets the caller pipeline chunks behind their gradient all-reduce.  opacity_reg / scale_reg
  * != 0 add the gradient of  opacity_reg * mean|sigmoid(raw opacity)| + scale_reg * mean|softplus(raw scale)[:3]|
  * (train.py:122-124; `[:3]` selects the first three primitives there and here).                               */
-int ubs_adam_step(int64_t N, int D, float *records, const float *grads, float *exp_avg, float *exp_avg_sq,
-                  const double *h_lr, double beta1, double beta2, double eps, int64_t step, double opacity_reg,
+int ubs_adam_step(int64_t N, int D, int64_t row_begin, int64_t row_count, /* update rows [begin, begin+count) of N */
+                  float *records, const float *grads, float *exp_avg, float *exp_avg_sq, const double *h_lr, double beta1, double beta2, double eps, int64_t step, double opacity_reg,
                   double scale_reg, void *stream);
 
 /* ubs_fused_project_bwd + ubs_adam_step in one launch, for single-GPU batch-1 training (the reference's default,

@@ -105,6 +105,20 @@ parallel.allreduce_gradients(v, world, batch_size=world)
 assert torch.allclose(v, expect, atol=1e-6), (v - expect).abs().max()
 w = parallel.allreduce_gradients(torch.ones(8), world, async_op=True)
 w.wait()
+# chunk-pipelined backward -> all-reduce -> per-chunk callback, with a stand-in for the rasteriser (host logic only)
+class FakeRasterizer:
+    N = 1000
+    def composite_backward(self, *a): self.composited = True
+    def project_backward_rows(self, records, vm, K, cp, ts, v_records, begin, count):
+        v_records[begin:begin + count] = records[begin:begin + count] * (rank + 1)
+rz = FakeRasterizer()
+rec = torch.arange(1000 * 4, dtype=torch.float32).reshape(1000, 4)
+out = torch.full((1000, 4), -1.0)
+seen = []
+parallel.pipelined_backward(rz, rec, None, None, None, None, None, None, None, out, world, None, 3,
+                            lambda b, c: seen.append((b, c)), batch_size=world)
+assert rz.composited and seen == parallel.row_chunks(1000, 3) and sum(c for _, c in seen) == 1000
+assert torch.allclose(out, rec * sum(r + 1 for r in range(world)) / world)
 cams = parallel.shard_cameras(7, world, rank)
 got = [None] * world
 dist.all_gather_object(got, cams)
@@ -112,6 +126,18 @@ assert sorted(sum(got, [])) == list(range(7))
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
+
+
+def test_row_chunks_cover_and_align():
+    from ubs_b200 import parallel
+
+    for N, k in ((3_000_000, 4), (1000, 3), (128, 4), (1, 4), (129, 2), (0, 4), (5000, 1)):
+        ch = parallel.row_chunks(N, k)
+        assert len(ch) <= max(k, 1) and sum(c for _, c in ch) == N
+        assert all(b % 128 == 0 and c > 0 for b, c in ch)
+        assert [b for b, _ in ch] == sorted(b for b, _ in ch)
+        if ch:
+            assert ch[0][0] == 0 and all(ch[i][0] + ch[i][1] == ch[i + 1][0] for i in range(len(ch) - 1))
 
 
 def test_gradient_allreduce_two_ranks_gloo(tmp_path):

@@ -256,3 +256,41 @@ def test_train_step_fused_and_unfused_agree():
     assert abs(out[0][1] - out[1][1]) < 1e-5
     # atomics in the compositing backward: rounding-level gradient noise, amplified only where a gradient ~ 0
     assert ((out[0][0] - out[1][0]).abs() > 1e-6).float().mean().item() < 1e-3
+
+
+def test_chunked_backward_and_row_range_adam_are_bit_identical_to_whole_buffer_calls():
+    """project_backward_rows over row chunks == one whole-buffer call, and Adam applied chunk by chunk (rows=...)
+    == one whole-buffer step: the pieces the multi-GPU pipeline (parallel.pipelined_backward) is made of."""
+    from ubs_b200 import fused, parallel, synth, training
+
+    D, N, W, H = 6, 25003, 320, 240
+    scene = synth.make_scene(N, D, seed=61).to("cuda")
+    cam = synth.make_cameras(1, W, H, seed=5, device="cuda")[0]
+    bg = torch.zeros(1, 3, device="cuda")
+    args = (cam.viewmat[None], cam.K[None], cam.cam_pos[None], None, bg)
+    rz = fused.FusedRasterizer(D, N, W, H, n_cams=1)
+    rec = fused.pack_records(D, *scene.tensors())
+    rz.forward(rec, *args)
+    v_rc = torch.randn(1, H, W, 3, device="cuda") / (W * H)
+    whole = rz.backward(rec, *args, v_rc, torch.zeros(1, H, W, 1, device="cuda")).clone()  # leaves rz.v_* filled
+    chunks = parallel.row_chunks(N, 5)
+    assert len(chunks) == 5
+    pieces = torch.full_like(whole, float("nan"))
+    for b, c in chunks:
+        rz.project_backward_rows(rec, *args[:4], pieces, b, c)
+    assert torch.equal(pieces, whole)
+    # world = 1 goes through the same code path as world > 1, minus the collective
+    seen = []
+    piped = parallel.pipelined_backward(rz, rec, *args, v_rc, torch.zeros(1, H, W, 1, device="cuda"),
+                                        torch.empty_like(whole), 1, None, 5, lambda b, c: seen.append((b, c)))
+    assert seen == [(0, N)]
+    assert ((piped - whole).abs() > 1e-6 * whole.abs().max()).float().mean().item() < 1e-3  # atomics in compositing
+
+    rec_a, rec_b = rec.clone(), rec.clone()
+    adam_a, adam_b = training.PackedAdam(D, N), training.PackedAdam(D, N)
+    for it in range(2):
+        adam_a.step(rec_a, whole, 0.01, 0.02)
+        for k, (b, c) in enumerate(chunks):
+            adam_b.step(rec_b, whole, 0.01, 0.02, rows=(b, c), advance=(k == 0))
+        assert adam_a.step_count == adam_b.step_count == it + 1
+        assert torch.equal(rec_a, rec_b) and torch.equal(adam_a.exp_avg_sq, adam_b.exp_avg_sq)

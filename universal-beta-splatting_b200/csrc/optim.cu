@@ -17,14 +17,15 @@ namespace ubs {
 namespace {
 
 __global__ void __launch_bounds__(256)
-adam_kernel(int64_t n_vec, int vec_per_row, float4 *__restrict__ params, const float4 *__restrict__ grads,
-            float4 *__restrict__ exp_avg, float4 *__restrict__ exp_avg_sq, AdamParams a) {
+adam_kernel(int64_t n_vec, int vec_per_row, int64_t row_begin, float4 *__restrict__ params,
+            const float4 *__restrict__ grads, float4 *__restrict__ exp_avg, float4 *__restrict__ exp_avg_sq,
+            AdamParams a) {
     __shared__ float s_step[kAdamMaxStride];
     if (threadIdx.x < kAdamMaxStride) s_step[threadIdx.x] = a.step_size[threadIdx.x];
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = i / vec_per_row;
-        const int c0 = (int)(i - row * vec_per_row) * 4;
+        const int64_t row_local = i / vec_per_row, row = row_begin + row_local;  // `row` = global primitive index
+        const int c0 = (int)(i - row_local * vec_per_row) * 4;
         float4 p4 = params[i], g4 = __ldcs(grads + i), m4 = exp_avg[i], v4 = exp_avg_sq[i];
         float p[4] = {p4.x, p4.y, p4.z, p4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
         float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -91,18 +92,21 @@ relocate_fixup_kernel(int64_t K, int stride, int col_opacity, float *__restrict_
 }  // namespace
 }  // namespace ubs
 
-extern "C" int ubs_adam_step(int64_t N, int D, float *records, const float *grads, float *exp_avg, float *exp_avg_sq,
-                             const double *h_lr, double beta1, double beta2, double eps, int64_t step,
+extern "C" int ubs_adam_step(int64_t N, int D, int64_t row_begin, int64_t row_count, float *records,
+                             const float *grads, float *exp_avg, float *exp_avg_sq, const double *h_lr, double beta1, double beta2, double eps, int64_t step,
                              double opacity_reg, double scale_reg, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(N >= 0 && D >= 4 && D <= 8, "adam_step: bad sizes (N=%lld, D=%d)", (long long)N, D);
-    if (N == 0) return UBS_OK;
+    UBS_CHECK_ARG(row_begin >= 0 && row_count >= 0 && row_begin + row_count <= N, "adam_step: rows [%lld, +%lld) outside N=%lld",
+                  (long long)row_begin, (long long)row_count, (long long)N);
+    if (N == 0 || row_count == 0) return UBS_OK;
     UBS_CHECK_ARG(records && grads && exp_avg && exp_avg_sq && h_lr, "adam_step: null pointer");
     UBS_CHECK_ARG(step >= 1, "adam_step: step counts from 1 (got %lld)", (long long)step);
     const int stride = UBS_RECORD_STRIDE(D);
     UBS_CHECK_ARG(stride <= kAdamMaxStride, "adam_step: stride %d exceeds %d", stride, kAdamMaxStride);
     const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
-    const int64_t n_vec = N * (stride / 4);
+    const int64_t n_vec = row_count * (stride / 4);
+    const size_t off = (size_t)row_begin * stride;
     int sm = 148;
     {
         int dev = 0;
@@ -111,8 +115,9 @@ extern "C" int ubs_adam_step(int64_t N, int D, float *records, const float *grad
     }
     const int64_t blocks = ceil_div(n_vec, 256);
     const unsigned grid = (unsigned)(blocks < (int64_t)sm * 16 ? blocks : (int64_t)sm * 16);
-    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_vec, stride / 4, (float4 *)records, (const float4 *)grads,
-                                                        (float4 *)exp_avg, (float4 *)exp_avg_sq, a);
+    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_vec, stride / 4, row_begin, (float4 *)(records + off),
+                                                        (const float4 *)(grads + off), (float4 *)(exp_avg + off),
+                                                        (float4 *)(exp_avg_sq + off), a);
     UBS_LAUNCH_CHECK("adam_kernel");
     return UBS_OK;
 }

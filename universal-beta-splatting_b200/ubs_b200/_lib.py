@@ -50,7 +50,7 @@ SIGNATURES = {
     "ubs_l1_ssim_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "ubs_l1_ssim_loss": (c_int, [c_int, c_int, c_int, c_int, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64,
                                  c_int64, c_int64, c_int64, c_float, c_float, _P, _P, _P, c_size_t, _P]),
-    "ubs_adam_step": (c_int, [c_int64, c_int, _P, _P, _P, _P, _P, c_double, c_double, c_double, c_int64, c_double,
+    "ubs_adam_step": (c_int, [c_int64, c_int, c_int64, c_int64, _P, _P, _P, _P, _P, c_double, c_double, c_double, c_int64, c_double,
                               c_double, _P]),
     "ubs_fused_project_bwd_adam": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_int] +
                                    [_P] * 11 + [c_double, c_double, c_double, c_int64, c_double, c_double, _P]),

@@ -234,17 +234,7 @@ class FusedRasterizer:
         `records` and the moments are updated in place, no gradient buffer is produced and None is returned."""
         lib, s = self.lib, torch.cuda.current_stream().cuda_stream
         C, N, D = self.C, self.N, self.D
-        self._grad_buffers().zero_()  # one memset for all five screen-space gradient arrays
-        v_rc = v_render_colors.contiguous()
-        v_ra = v_render_alphas.contiguous()
-        assert v_rc.shape == (C, self.H, self.W, 3) and v_ra.shape == (C, self.H, self.W, 1)
-        with self._stage("rasterize_bwd"):
-          check(lib.ubs_rasterize_bwd(
-            C, N, ptr(self.n_isects), self.capacity, ptr(self.means2d), ptr(self.conics), ptr(self.colors),
-            ptr(self.opacities), ptr(self.betas), ptr(backgrounds), None, 3, self.W, self.H, self.tile_size,
-            ptr(self.offsets), ptr(self.flatten_ids), ptr(self.render_alphas), ptr(self.last_ids), ptr(v_rc),
-            ptr(v_ra), ptr(self.v_means2d), ptr(self.v_conics), ptr(self.v_colors), ptr(self.v_opacities),
-            ptr(self.v_betas), s), "ubs_rasterize_bwd")
+        self.composite_backward(backgrounds, v_render_colors, v_render_alphas)
         if adam is not None:
             # single-GPU batch-1 training: projection backward + Adam in one launch, records updated in place
             import ctypes
@@ -262,11 +252,39 @@ class FusedRasterizer:
         if v_records is None:
             v_records = torch.empty_like(records)
         with self._stage("fused_project_bwd"):
-          check(lib.ubs_fused_project_bwd(
-            C, N, D, ptr(records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), self.W, self.H, self.eps2d,
-            1 if self.aa else 0, ptr(self.radii), ptr(self.conics), ptr(self.v_means2d), None, ptr(self.v_conics),
-            ptr(self.v_opacities), ptr(self.v_betas), ptr(self.v_colors), ptr(v_records), s), "ubs_fused_project_bwd")
+            self.project_backward_rows(records, viewmats, Ks, cam_pos, timestamps, v_records, 0, N)
         return v_records
+
+    @torch.no_grad()
+    def composite_backward(self, backgrounds: Optional[Tensor], v_render_colors: Tensor, v_render_alphas: Tensor):
+        """First half of backward(): screen-space gradients of the most recent forward() into self.v_*."""
+        lib, s = self.lib, torch.cuda.current_stream().cuda_stream
+        C, N = self.C, self.N
+        self._grad_buffers().zero_()  # one memset for all five screen-space gradient arrays
+        v_rc, v_ra = v_render_colors.contiguous(), v_render_alphas.contiguous()
+        assert v_rc.shape == (C, self.H, self.W, 3) and v_ra.shape == (C, self.H, self.W, 1)
+        with self._stage("rasterize_bwd"):
+          check(lib.ubs_rasterize_bwd(
+            C, N, ptr(self.n_isects), self.capacity, ptr(self.means2d), ptr(self.conics), ptr(self.colors),
+            ptr(self.opacities), ptr(self.betas), ptr(backgrounds), None, 3, self.W, self.H, self.tile_size,
+            ptr(self.offsets), ptr(self.flatten_ids), ptr(self.render_alphas), ptr(self.last_ids), ptr(v_rc),
+            ptr(v_ra), ptr(self.v_means2d), ptr(self.v_conics), ptr(self.v_colors), ptr(self.v_opacities),
+            ptr(self.v_betas), s), "ubs_rasterize_bwd")
+
+    @torch.no_grad()
+    def project_backward_rows(self, records, viewmats, Ks, cam_pos, timestamps, v_records, begin: int, count: int):
+        """Second half of backward() for primitives [begin, begin + count): gradient records of those rows from
+        self.v_*.  Row ranges are independent, so a caller can pipeline them against a collective (one camera)."""
+        assert self.C == 1 or (begin == 0 and count == self.N), "row ranges need the [C, N] arrays to be [1, N]"
+        if count == 0:
+            return
+        sl = slice(begin, begin + count)
+        check(self.lib.ubs_fused_project_bwd(
+            self.C, count, self.D, ptr(records[sl]), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), self.W,
+            self.H, self.eps2d, 1 if self.aa else 0, ptr(self.radii[:, sl]), ptr(self.conics[:, sl]),
+            ptr(self.v_means2d[:, sl]), None, ptr(self.v_conics[:, sl]), ptr(self.v_opacities[:, sl]),
+            ptr(self.v_betas[:, sl]), ptr(self.v_colors[:, sl]), ptr(v_records[sl]),
+            torch.cuda.current_stream().cuda_stream), "ubs_fused_project_bwd")
 
 
 class HostPipeline:

@@ -151,17 +151,22 @@ class PackedAdam:
         return cols
 
     @torch.no_grad()
-    def step(self, records: Tensor, grads: Tensor, opacity_reg: float = 0.0, scale_reg: float = 0.0):
+    def step(self, records: Tensor, grads: Tensor, opacity_reg: float = 0.0, scale_reg: float = 0.0, rows=None,
+             advance: bool = True):
         """In-place update of `records` (and the moments) from `grads` ([N, stride], e.g. FusedRasterizer.backward's
-        output).  opacity_reg / scale_reg: coefficients of the regularisers of train.py:122-124 (0 = off)."""
+        output).  opacity_reg / scale_reg: coefficients of the regularisers of train.py:122-124 (0 = off).
+        rows = (begin, count) restricts the update to a row range (one optimiser step applied chunk by chunk:
+        pass advance=False for every chunk after the first)."""
         N = records.shape[0]
         assert records.shape == (N, self.stride) and grads.shape == records.shape == self.exp_avg.shape
         assert records.is_cuda and records.is_contiguous() and grads.is_contiguous()
-        self.step_count += 1
+        if advance:
+            self.step_count += 1
+        begin, count = (0, N) if rows is None else rows
         cols = (ctypes.c_double * self.stride)(*self.lr_columns())
-        check(self.lib.ubs_adam_step(N, self.D, ptr(records), ptr(grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                                     ctypes.cast(cols, ctypes.c_void_p), self.betas[0], self.betas[1], self.eps,
-                                     self.step_count, float(opacity_reg), float(scale_reg),
+        check(self.lib.ubs_adam_step(N, self.D, begin, count, ptr(records), ptr(grads), ptr(self.exp_avg),
+                                     ptr(self.exp_avg_sq), ctypes.cast(cols, ctypes.c_void_p), self.betas[0],
+                                     self.betas[1], self.eps, self.step_count, float(opacity_reg), float(scale_reg),
                                      torch.cuda.current_stream().cuda_stream), "ubs_adam_step")
 
     def grow(self, n_new: int):
@@ -218,8 +223,9 @@ class TrainStep:
     forward -> L1+SSIM loss and its image gradient -> backward -> (all-reduce) -> Adam.  Zero host syncs."""
 
     def __init__(self, rz: FusedRasterizer, adam: PackedAdam, lambda_dssim: float = 0.2, world: int = 1, group=None,
-                 fuse_adam: bool = True):
+                 fuse_adam: bool = True, n_chunks: int = 4):
         assert rz.C == 1
+        self.n_chunks = n_chunks
         self.rz, self.adam, self.lam, self.world, self.group = rz, adam, lambda_dssim, world, group
         # one view per optimiser step on one GPU (the reference's default batch_size = 1): nothing to sum before the
         # update, so Adam rides in the projection-backward kernel and the gradient records never reach HBM
@@ -248,9 +254,15 @@ class TrainStep:
             rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, self.v_rc, self.v_ra, None, self.adam,
                         opacity_reg, scale_reg)
             return self.loss_out
-        rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, self.v_rc, self.v_ra, self.v_records)
-        with rz._stage("allreduce"):
-            parallel.allreduce_gradients(self.v_records, self.world, None, self.group)
-        with rz._stage("adam_step"):
-            self.adam.step(records, self.v_records, opacity_reg, scale_reg)
+        # world > 1: the projection backward runs chunk by chunk; chunk k's gradient all-reduce (NCCL, its own stream)
+        # overlaps the backward of chunk k+1 and the Adam update of chunk k-1
+        adam, first = self.adam, [True]
+
+        def after_reduce(begin, count):
+            adam.step(records, self.v_records, opacity_reg, scale_reg, rows=(begin, count), advance=first[0])
+            first[0] = False
+
+        with rz._stage("bwd_allreduce_adam"):
+            parallel.pipelined_backward(rz, records, viewmats, Ks, cam_pos, timestamps, backgrounds, self.v_rc,
+                                        self.v_ra, self.v_records, self.world, self.group, self.n_chunks, after_reduce)
         return self.loss_out
