@@ -4,6 +4,8 @@
 // -- rahul-goel/fused-ssim@1272e21, absent from the reference tree -- whose published algorithm is the same SSIM:
 // 11x11 Gaussian window, sigma 1.5, zero "same" padding, C1 = 0.01^2, C2 = 0.03^2, mean over all elements).
 //
+// Both kernels fetch the next channel's input tiles into registers while the current channel is convolved (the
+// staging loads were the exposed latency: long-scoreboard 42 % / 63 % of the stall samples before, 279 -> 169 us).
 // Kernel 1 (ssim_fwd): per 32x32 tile and channel, the five windowed moments E[x], E[x^2], E[y], E[y^2], E[xy] by a
 // separable convolution out of shared memory with register sliding windows (each thread produces a strip of
 // outputs from one strip of loads), then the SSIM value and its three partial derivatives w.r.t. the moments of x
@@ -38,19 +40,32 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// stage a kIN x kIN tile (zero outside the image) of one (camera, channel) plane
-__device__ __forceinline__ void stage_tile(float (*dst)[kIN + 1], const float *plane, int64_t sy, int64_t sx, int H,
-                                           int W, int y0, int x0) {
-    for (int idx = threadIdx.x; idx < kIN * kIN; idx += kThreads) {
-        const int r = idx / kIN, c = idx - r * kIN;
-        const int gy = y0 - kR + r, gx = x0 - kR + c;
-        float v = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = plane[gy * sy + gx * sx];
-        dst[r][c] = v;
+// stage a kIN x kIN tile (zero outside the image) of one (camera, channel) plane: the global loads go to registers
+// first (issued a whole phase before they are needed) and to shared memory later
+constexpr int kStageRegs = (kIN * kIN + kThreads - 1) / kThreads;  // 7
+
+__device__ __forceinline__ void tile_load(float (&r)[kStageRegs], const float *plane, int64_t sy, int64_t sx, int H,
+                                          int W, int y0, int x0) {
+#pragma unroll
+    for (int j = 0; j < kStageRegs; ++j) {
+        const int idx = threadIdx.x + j * kThreads;
+        const int row = idx / kIN, c = idx - row * kIN;
+        const int gy = y0 - kR + row, gx = x0 - kR + c;
+        r[j] = (idx < kIN * kIN && gy >= 0 && gy < H && gx >= 0 && gx < W) ? plane[gy * sy + gx * sx] : 0.f;
+    }
+}
+__device__ __forceinline__ void tile_store(float (*dst)[kIN + 1], const float (&r)[kStageRegs]) {
+#pragma unroll
+    for (int j = 0; j < kStageRegs; ++j) {
+        const int idx = threadIdx.x + j * kThreads;
+        const int row = idx / kIN, c = idx - row * kIN;
+        if (idx < kIN * kIN) dst[row][c] = r[j];
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+// two CTAs per SM: the prefetch registers do not fit the 80-register budget of three (148 B of spills, 175 us against
+// 169 us for loss + gradient at 1080p)
+__global__ void __launch_bounds__(kThreads, 2)
 ssim_fwd_kernel(int CH, int H, int W, ImageView img, ImageView gt, Window win, float *__restrict__ maps,
                 double *__restrict__ sums) {
     __shared__ float s_x[kIN][kIN + 1], s_y[kIN][kIN + 1];
@@ -62,11 +77,18 @@ ssim_fwd_kernel(int CH, int H, int W, ImageView img, ImageView gt, Window win, f
     float l1_acc = 0.f, ssim_acc = 0.f;
     constexpr float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
 
+    float rx[kStageRegs], ry[kStageRegs];
+    tile_load(rx, img.base + cam * img.sn, img.sy, img.sx, H, W, y0, x0);
+    tile_load(ry, gt.base + cam * gt.sn, gt.sy, gt.sx, H, W, y0, x0);
     for (int ch = 0; ch < CH; ++ch) {
         __syncthreads();  // previous channel's vertical pass has finished reading s_h / s_x / s_y
-        stage_tile(s_x, img.base + cam * img.sn + ch * img.sc, img.sy, img.sx, H, W, y0, x0);
-        stage_tile(s_y, gt.base + cam * gt.sn + ch * gt.sc, gt.sy, gt.sx, H, W, y0, x0);
+        tile_store(s_x, rx);
+        tile_store(s_y, ry);
         __syncthreads();
+        if (ch + 1 < CH) {  // next channel's tile: in flight during both passes of this one
+            tile_load(rx, img.base + cam * img.sn + (ch + 1) * img.sc, img.sy, img.sx, H, W, y0, x0);
+            tile_load(ry, gt.base + cam * gt.sn + (ch + 1) * gt.sc, gt.sy, gt.sx, H, W, y0, x0);
+        }
         // horizontal pass: item = (row, strip of 8 output columns); 18 loads per image feed 8 outputs x 11 taps
         if (tid < kIN * (kTX / 8)) {
             const int row = tid % kIN, c0 = (tid / kIN) * 8;
@@ -155,40 +177,66 @@ ssim_fwd_kernel(int CH, int H, int W, ImageView img, ImageView gt, Window win, f
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 ssim_bwd_kernel(int CH, int H, int W, ImageView img, ImageView gt, Window win, const float *__restrict__ maps,
                 float l1_coeff, float ssim_coeff, float *__restrict__ v_img) {
-    __shared__ float s_m[kIN][kIN + 1];
-    __shared__ float s_h[kIN][kTX + 1];
+    __shared__ float s_m[3][kIN][kIN + 1];
+    __shared__ float s_h[3][kIN][kTX + 1];
     const int cam = blockIdx.z, x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
     const int tid = threadIdx.x;
     const size_t plane_elems = (size_t)H * W;
     const int col = tid & 31, r0 = (tid >> 5) * 4;
     const int gx = x0 + col;
 
+    float rm[3][kStageRegs];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+        tile_load(rm[q], maps + ((size_t)(cam * CH) * 3 + q) * plane_elems, (int64_t)W, 1, H, W, y0, x0);
     for (int ch = 0; ch < CH; ++ch) {
-        float conv[3][4];
-        for (int q = 0; q < 3; ++q) {
-            __syncthreads();
-            stage_tile(s_m, maps + ((size_t)(cam * CH + ch) * 3 + q) * plane_elems, (int64_t)W, 1, H, W, y0, x0);
-            __syncthreads();
-            if (tid < kIN * (kTX / 8)) {
-                const int row = tid % kIN, c0 = (tid / kIN) * 8;
-                float v[8 + 2 * kR];
+        __syncthreads();  // previous channel's passes have finished reading s_m / s_h
 #pragma unroll
-                for (int k = 0; k < 8 + 2 * kR; ++k) v[k] = s_m[row][c0 + k];
+        for (int q = 0; q < 3; ++q) tile_store(s_m[q], rm[q]);
+        __syncthreads();
+        if (ch + 1 < CH) {  // the next channel's three maps: in flight during this channel's passes
 #pragma unroll
-                for (int o = 0; o < 8; ++o) {
-                    float a = 0.f;
+            for (int q = 0; q < 3; ++q)
+                tile_load(rm[q], maps + ((size_t)(cam * CH + ch + 1) * 3 + q) * plane_elems, (int64_t)W, 1, H, W, y0, x0);
+        }
+        // the pixel's own values for the epilogue, also early
+        float xv[4], yv[4];
+        {
+            const float *xp = img.base + cam * img.sn + ch * img.sc;
+            const float *yp = gt.base + cam * gt.sn + ch * gt.sc;
 #pragma unroll
-                    for (int k = 0; k < 2 * kR + 1; ++k) a = fmaf(win.g[k], v[o + k], a);
-                    s_h[row][c0 + o] = a;
-                }
+            for (int o = 0; o < 4; ++o) {
+                const int gy = y0 + r0 + o;
+                const bool in = gx < W && gy < H;
+                xv[o] = in ? xp[gy * img.sy + gx * img.sx] : 0.f;
+                yv[o] = in ? yp[gy * gt.sy + gx * gt.sx] : 0.f;
             }
-            __syncthreads();
+        }
+        // horizontal pass over the three maps: item = (map, row, strip of 8 columns)
+        for (int item = tid; item < 3 * kIN * (kTX / 8); item += kThreads) {
+            const int q = item / (kIN * (kTX / 8)), rem = item - q * (kIN * (kTX / 8));
+            const int row = rem % kIN, c0 = (rem / kIN) * 8;
+            float v[8 + 2 * kR];
+#pragma unroll
+            for (int k = 0; k < 8 + 2 * kR; ++k) v[k] = s_m[q][row][c0 + k];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 2 * kR + 1; ++k) a = fmaf(win.g[k], v[o + k], a);
+                s_h[q][row][c0 + o] = a;
+            }
+        }
+        __syncthreads();
+        float conv[3][4];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
             float v[4 + 2 * kR];
 #pragma unroll
-            for (int k = 0; k < 4 + 2 * kR; ++k) v[k] = s_h[r0 + k][col];
+            for (int k = 0; k < 4 + 2 * kR; ++k) v[k] = s_h[q][r0 + k][col];
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
                 float a = 0.f;
@@ -198,13 +246,11 @@ ssim_bwd_kernel(int CH, int H, int W, ImageView img, ImageView gt, Window win, c
             }
         }
         if (gx < W) {
-            const float *xp = img.base + cam * img.sn + ch * img.sc;
-            const float *yp = gt.base + cam * gt.sn + ch * gt.sc;
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
                 const int gy = y0 + r0 + o;
                 if (gy < H) {
-                    const float x = xp[gy * img.sy + gx * img.sx], y = yp[gy * gt.sy + gx * gt.sx];
+                    const float x = xv[o], y = yv[o];
                     const float d = x - y;
                     const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
                     const float ds = conv[0][o] + 2.f * x * conv[1][o] + y * conv[2][o];
