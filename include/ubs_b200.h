@@ -31,6 +31,7 @@ extern "C" {
 #define UBS_EUNSUPPORTED (-4)
 
 #define UBS_MAX_CHANNELS 16 /* colour channels handled by one compositing launch      */
+#define UBS_MAX_RANKS 8     /* GPUs of one NVSwitch box in the sharded train step     */
 
 /* ---- library ------------------------------------------------------------------------------------------ */
 const char *ubs_last_error(void);
@@ -283,6 +284,27 @@ int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *records, const fl
                                const float *v_opacities, const float *v_betas, const float *v_colors, float *exp_avg,
                                float *exp_avg_sq, const double *h_lr, double beta1, double beta2, double eps,
                                int64_t step, double opacity_reg, double scale_reg, void *stream);
+
+/* ---- sharded train step over the GPUs of one NVSwitch box (no reference counterpart: SURVEY.md 2.3) ------------ */
+/* Rows are split into `world` shards of `shard_rows` (a multiple of 128) rows; rank g owns shard g, i.e. its Adam
+ * moments and the duty to update its parameters.  Pointers in the h_* arrays are HOST arrays of `world` DEVICE
+ * addresses of symmetric (peer-mapped) buffers, entry g = rank g's buffer.
+ *
+ * ubs_fused_project_bwd_scatter: ubs_fused_project_bwd for one camera whose gradient tiles go, by bulk stores over
+ * NVLink, into slot `rank` of the owner's staging buffer [world][shard_rows][stride] instead of a local v_records.
+ * ubs_reduce_adam_gather: the owner sums the `world` slots of its staging buffer, applies ubs_adam_step's update to
+ * its rows (moments are [shard_rows, stride], local) and stores the new parameters into every rank's records.
+ * The caller separates the two, and the next forward, with a barrier across the ranks.                            */
+int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *records, const float *viewmats, const float *Ks,
+                                  const float *cam_pos, const float *timestamps, int width, int height, float eps2d,
+                                  int calc_compensations, const int32_t *radii, const float *conics,
+                                  const float *v_means2d, const float *v_depths, const float *v_conics,
+                                  const float *v_opacities, const float *v_betas, const float *v_colors, int world,
+                                  int rank, int64_t shard_rows, float *const *h_staging, void *stream);
+int ubs_reduce_adam_gather(int64_t N, int D, int world, int rank, int64_t shard_rows, const float *staging,
+                           float *exp_avg_shard, float *exp_avg_sq_shard, float *const *h_peer_records,
+                           const double *h_lr, double beta1, double beta2, double eps, int64_t step,
+                           double opacity_reg, double scale_reg, void *stream);
 
 /* MCMC relocation given the sampled indices: rows dst_idx[i] <- rows src_idx[i] with the opacity rescaled to
  * 1 - (1 - o)^(1/(m+1)), m = multiplicity of the source among src_idx, clamped to [0.005, 1 - eps]; the sources

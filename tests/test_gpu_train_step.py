@@ -294,3 +294,49 @@ def test_chunked_backward_and_row_range_adam_are_bit_identical_to_whole_buffer_c
             adam_b.step(rec_b, whole, 0.01, 0.02, rows=(b, c), advance=(k == 0))
         assert adam_a.step_count == adam_b.step_count == it + 1
         assert torch.equal(rec_a, rec_b) and torch.equal(adam_a.exp_avg_sq, adam_b.exp_avg_sq)
+
+
+@pytest.mark.parametrize("world,D,N", [(2, 6, 10007), (3, 7, 6500), (1, 6, 4000)])
+def test_sharded_step_kernels_equal_allreduce_then_adam_bitwise(world, D, N):
+    """The multi-GPU sharded step (projection backward scattering gradient tiles into the owners' staging slots,
+    owner-side reduce + Adam + parameter gather) with all ranks simulated in ONE process on ordinary tensors -- the
+    kernels only see device addresses -- against: per-rank gradient records summed in rank order, then the
+    whole-buffer Adam.  Bit-identical parameters on every rank, moments equal shard by shard."""
+    from ubs_b200 import fused, parallel, synth, training
+
+    W, H = 256, 192
+    scene = synth.make_scene(N, D, seed=70 + world).to("cuda")
+    cams = synth.make_cameras(world, W, H, seed=6, timestamps=[0.1 * (k + 1) for k in range(world)], device="cuda")
+    bg = torch.zeros(1, 3, device="cuda")
+    rec0 = fused.pack_records(D, *scene.tensors())
+    states = parallel.ShardedState.create_local_group(D, N, world)
+    for st in states:
+        st.records.copy_(rec0)
+        assert st.shard_rows % 128 == 0 and st.shard_rows * world >= N
+    rzs = [fused.FusedRasterizer(D, N, W, H, n_cams=1) for _ in range(world)]
+    ref_rec = rec0.clone()
+    ref_adam = training.PackedAdam(D, N)
+    adams = [training.PackedAdam(D, N, allocate_moments=False) for _ in range(world)]
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for it in range(3):
+        total = torch.zeros_like(ref_rec)
+        for r, (st, rz, cam) in enumerate(zip(states, rzs, cams)):
+            ts = torch.tensor([cam.timestamp], device="cuda") if D == 7 else None
+            args = (cam.viewmat[None], cam.K[None], cam.cam_pos[None], ts)
+            rz.forward(st.records, *args, bg)
+            v_rc = torch.randn(1, H, W, 3, device="cuda", generator=g) / (W * H)
+            rz.composite_backward(bg, v_rc, torch.zeros(1, H, W, 1, device="cuda"))
+            parallel.sharded_backward_scatter(rz, st, *args)
+            whole = torch.empty_like(ref_rec)
+            rz.project_backward_rows(st.records, *args, whole, 0, N)  # same screen-space gradients, plain layout
+            total = total + whole
+        # every slot of every staging buffer now holds that rank's rows
+        for r, st in enumerate(states):
+            parallel.sharded_reduce_adam_gather(st, adams[r], 0.01, 0.02)
+        ref_adam.step(ref_rec, total, 0.01, 0.02)
+        for r, st in enumerate(states):
+            assert torch.equal(st.records, ref_rec), (it, r)
+            b, n = st.my_rows()
+            assert torch.equal(st.exp_avg[:n], ref_adam.exp_avg[b:b + n]), (it, r)
+            assert torch.equal(st.exp_avg_sq[:n], ref_adam.exp_avg_sq[b:b + n]), (it, r)
+            assert float(st.exp_avg[n:].abs().sum()) == 0.0  # padding rows of the last shard never move

@@ -218,6 +218,13 @@ __device__ __forceinline__ void tma_bulk_commit_wait() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// Destination of the gradient tiles when the rows are sharded over the ranks of one NVSwitch box.
+struct ScatterDst {
+    float *staging[UBS_MAX_RANKS];  // staging[g] = rank g's [world][shard_rows][stride] buffer (peer-mapped)
+    int64_t shard_rows;             // 0 = plain v_records
+    int rank;
+};
+
 // Backward of fused_project_fwd_kernel: one thread per primitive, looping over cameras, so the per-primitive sums
 // need no atomics.  Recomputes the cheap forward intermediates from the record instead of storing them.
 //
@@ -236,7 +243,7 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
                          const float *__restrict__ v_conics, const float *__restrict__ v_opacities,
                          const float *__restrict__ v_betas, const float *__restrict__ v_colors,
                          float *__restrict__ v_records, float *__restrict__ exp_avg,
-                         float *__restrict__ exp_avg_sq, const AdamParams adam) {
+                         float *__restrict__ exp_avg_sq, const AdamParams adam, const ScatterDst scatter) {
     constexpr int Cd = D - 3, M = NdDims<D>::M;
     constexpr int STRIDE = UBS_RECORD_STRIDE(D);
     extern __shared__ __align__(128) float s_tiles[];  // [records][exp_avg][exp_avg_sq] (the last two with ADAM)
@@ -510,7 +517,16 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x == 0) tma_bulk_s2g(v_records + base * STRIDE, s_rec, bytes);
+    if (threadIdx.x == 0) {
+        float *dst = v_records + base * STRIDE;
+        if (scatter.shard_rows > 0) {
+            // multi-GPU scatter: this CTA's 128 rows belong to one owner rank (shard_rows is a multiple of 128); the
+            // tile goes straight into this rank's slot of the owner's staging buffer -- a peer address over NVLink
+            const int64_t owner = base / scatter.shard_rows, local = base - owner * scatter.shard_rows;
+            dst = scatter.staging[owner] + ((int64_t)scatter.rank * scatter.shard_rows + local) * STRIDE;
+        }
+        tma_bulk_s2g(dst, s_rec, bytes);
+    }
 }
 
 }  // namespace
@@ -591,16 +607,17 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
     // spill-free 255-register build at 3M primitives -- the kernel is latency bound, occupancy wins
     const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams unused{};
+    const ScatterDst no_scatter{};
     if (D == 6)
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records,
-            nullptr, nullptr, unused);
+            nullptr, nullptr, unused, no_scatter);
     else
         fused_project_bwd_kernel<7, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records,
-            nullptr, nullptr, unused);
+            nullptr, nullptr, unused, no_scatter);
     UBS_LAUNCH_CHECK("fused_project_bwd_kernel");
     return UBS_OK;
 }
@@ -636,7 +653,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
         fused_project_bwd_kernel<6, 3, true><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
-            exp_avg, exp_avg_sq, a);
+            exp_avg, exp_avg_sq, a, ScatterDst{});
     } else {
         UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<7, 3, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -645,8 +662,53 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
         fused_project_bwd_kernel<7, 3, true><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
-            exp_avg, exp_avg_sq, a);
+            exp_avg, exp_avg_sq, a, ScatterDst{});
     }
     UBS_LAUNCH_CHECK("fused_project_bwd_adam_kernel");
+    return UBS_OK;
+}
+
+extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *records, const float *viewmats,
+                                             const float *Ks, const float *cam_pos, const float *timestamps,
+                                             int width, int height, float eps2d, int calc_compensations,
+                                             const int32_t *radii, const float *conics, const float *v_means2d,
+                                             const float *v_depths, const float *v_conics, const float *v_opacities,
+                                             const float *v_betas, const float *v_colors, int world, int rank,
+                                             int64_t shard_rows, float *const *h_staging, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(N >= 0 && width > 0 && height > 0, "fused_project_bwd_scatter: bad sizes");
+    UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd_scatter: D must be 6 or 7 (got %d)", D);
+    UBS_CHECK_ARG(world >= 1 && world <= UBS_MAX_RANKS && rank >= 0 && rank < world,
+                  "fused_project_bwd_scatter: rank %d of %d (at most %d ranks)", rank, world, UBS_MAX_RANKS);
+    UBS_CHECK_ARG(shard_rows > 0 && shard_rows % kFusedThreads == 0 && shard_rows * world >= N,
+                  "fused_project_bwd_scatter: shard_rows must be a positive multiple of %d covering N", kFusedThreads);
+    if (N == 0) return UBS_OK;
+    UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && conics && v_means2d && v_conics && v_opacities &&
+                      v_betas && h_staging,
+                  "fused_project_bwd_scatter: null pointer");
+    UBS_CHECK_ARG(D != 7 || timestamps != nullptr, "fused_project_bwd_scatter: D=7 needs timestamps");
+    ScatterDst sc{};
+    for (int g = 0; g < world; ++g) {
+        UBS_CHECK_ARG(h_staging[g] != nullptr && ((uintptr_t)h_staging[g] & 15) == 0,
+                      "fused_project_bwd_scatter: staging[%d] null or not 16-byte aligned", g);
+        sc.staging[g] = h_staging[g];
+    }
+    sc.shard_rows = shard_rows;
+    sc.rank = rank;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
+    const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
+    const AdamParams unused{};
+    if (D == 6)
+        fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
+            1, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
+            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
+            nullptr, nullptr, unused, sc);
+    else
+        fused_project_bwd_kernel<7, 3, false><<<gx, kFusedThreads, smem, s>>>(
+            1, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
+            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
+            nullptr, nullptr, unused, sc);
+    UBS_LAUNCH_CHECK("fused_project_bwd_scatter_kernel");
     return UBS_OK;
 }

@@ -40,6 +40,44 @@ adam_kernel(int64_t n_vec, int vec_per_row, int64_t row_begin, float4 *__restric
     }
 }
 
+struct PeerRecords {
+    float4 *p[UBS_MAX_RANKS];
+};
+
+// Owner side of the sharded step: rows [row_begin, row_begin + n_rows) belong to this rank.  Their gradient is the sum
+// of the `world` staging slots (fixed order: every rank would compute the same bits), Adam runs on the shard's
+// moments, and the new parameters are stored into every rank's record buffer (peer addresses over NVLink).
+__global__ void __launch_bounds__(256)
+reduce_adam_gather_kernel(int64_t n_vec, int vec_per_row, int64_t row_begin, int world, int64_t slot_vecs,
+                          const float4 *__restrict__ staging, float4 *__restrict__ exp_avg,
+                          float4 *__restrict__ exp_avg_sq, PeerRecords peers, int rank, AdamParams a) {
+    __shared__ float s_step[kAdamMaxStride];
+    if (threadIdx.x < kAdamMaxStride) s_step[threadIdx.x] = a.step_size[threadIdx.x];
+    __syncthreads();
+    const int64_t rec_off = row_begin * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row_local = i / vec_per_row, row = row_begin + row_local;
+        const int c0 = (int)(i - row_local * vec_per_row) * 4;
+        float4 g4 = __ldcs(staging + i);
+        for (int j = 1; j < world; ++j) {
+            const float4 t = __ldcs(staging + j * slot_vecs + i);
+            g4.x += t.x, g4.y += t.y, g4.z += t.z, g4.w += t.w;
+        }
+        float4 p4 = peers.p[rank][rec_off + i], m4 = exp_avg[i], v4 = exp_avg_sq[i];
+        float p[4] = {p4.x, p4.y, p4.z, p4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+        float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            g[k] += adam_reg_grad(a, row, c0 + k, p[k]);
+            adam_update(a, s_step[c0 + k], p[k], g[k], m[k], v[k]);
+        }
+        exp_avg[i] = make_float4(m[0], m[1], m[2], m[3]);
+        exp_avg_sq[i] = make_float4(v[0], v[1], v[2], v[3]);
+        const float4 out = make_float4(p[0], p[1], p[2], p[3]);
+        for (int j = 0; j < world; ++j) peers.p[j][rec_off + i] = out;
+    }
+}
+
 __global__ void count_sources_kernel(int64_t K, const int64_t *__restrict__ src, int32_t *__restrict__ counts) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < K) atomicAdd(counts + src[i], 1);
@@ -139,5 +177,43 @@ extern "C" int ubs_mcmc_relocate(int64_t N, int D, float *records, float *exp_av
     UBS_LAUNCH_CHECK("relocate_copy_kernel");
     relocate_fixup_kernel<<<grid, 256, 0, s>>>(K, stride, col_opacity, records, exp_avg, exp_avg_sq, dst_idx, src_idx);
     UBS_LAUNCH_CHECK("relocate_fixup_kernel");
+    return UBS_OK;
+}
+
+extern "C" int ubs_reduce_adam_gather(int64_t N, int D, int world, int rank, int64_t shard_rows, const float *staging,
+                                      float *exp_avg_shard, float *exp_avg_sq_shard, float *const *h_peer_records,
+                                      const double *h_lr, double beta1, double beta2, double eps, int64_t step,
+                                      double opacity_reg, double scale_reg, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(N >= 0 && D >= 4 && D <= 8, "reduce_adam_gather: bad sizes (N=%lld, D=%d)", (long long)N, D);
+    UBS_CHECK_ARG(world >= 1 && world <= UBS_MAX_RANKS && rank >= 0 && rank < world,
+                  "reduce_adam_gather: rank %d of %d (at most %d ranks)", rank, world, UBS_MAX_RANKS);
+    UBS_CHECK_ARG(shard_rows > 0 && shard_rows * world >= N, "reduce_adam_gather: shards do not cover N");
+    UBS_CHECK_ARG(step >= 1, "reduce_adam_gather: step counts from 1 (got %lld)", (long long)step);
+    UBS_CHECK_ARG(staging && exp_avg_shard && exp_avg_sq_shard && h_peer_records && h_lr,
+                  "reduce_adam_gather: null pointer");
+    const int64_t row_begin = (int64_t)rank * shard_rows;
+    const int64_t n_rows = N - row_begin < shard_rows ? N - row_begin : shard_rows;
+    if (n_rows <= 0) return UBS_OK;  // this rank's shard is all padding
+    const int stride = UBS_RECORD_STRIDE(D);
+    PeerRecords peers{};
+    for (int g = 0; g < world; ++g) {
+        UBS_CHECK_ARG(h_peer_records[g] != nullptr, "reduce_adam_gather: peer_records[%d] is null", g);
+        peers.p[g] = (float4 *)h_peer_records[g];
+    }
+    const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
+    const int64_t n_vec = n_rows * (stride / 4);
+    int sm = 148;
+    {
+        int dev = 0;
+        UBS_CUDA_TRY(cudaGetDevice(&dev));
+        UBS_CUDA_TRY(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int64_t blocks = ceil_div(n_vec, 256);
+    const unsigned grid = (unsigned)(blocks < (int64_t)sm * 16 ? blocks : (int64_t)sm * 16);
+    reduce_adam_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        n_vec, stride / 4, row_begin, world, shard_rows * (stride / 4), (const float4 *)staging, (float4 *)exp_avg_shard,
+        (float4 *)exp_avg_sq_shard, peers, rank, a);
+    UBS_LAUNCH_CHECK("reduce_adam_gather_kernel");
     return UBS_OK;
 }

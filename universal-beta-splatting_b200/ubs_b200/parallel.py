@@ -77,6 +77,116 @@ def pipelined_backward(rz, records, viewmats, Ks, cam_pos, timestamps, backgroun
     return v_records
 
 
+class ShardedState:
+    """Buffers of the sharded train step: rows are split into `world` shards of `shard_rows` (a multiple of 128);
+    rank g owns shard g -- its Adam moments live only there -- and every rank keeps a full copy of the parameters.
+
+      records  [N, stride]                    this rank's parameters, in symmetric (peer-mapped) memory: the owners
+                                              of the other shards store updated rows into it over NVLink
+      staging  [world, shard_rows, stride]    slot j = rank j's gradient contribution to MY shard, written by rank
+                                              j's projection-backward kernel
+      exp_avg / exp_avg_sq [shard_rows, stride]   local
+
+    `create` allocates with torch.distributed._symmetric_memory (one process per GPU); `create_local_group` builds
+    all ranks' states inside ONE process from ordinary tensors -- the kernels only see device addresses -- which is
+    how the single-GPU tests exercise the multi-rank logic bit for bit."""
+
+    def __init__(self, D, N, world, rank, records_buf, staging_buf, peer_records, peer_staging, barrier):
+        from .fused import record_stride
+
+        self.D, self.N, self.world, self.rank = D, N, world, rank
+        self.stride = record_stride(D)
+        self.shard_rows = shard_rows_for(N, world)
+        self._records_buf, self._staging_buf = records_buf, staging_buf
+        self.records = records_buf[:N * self.stride].view(N, self.stride)
+        self.staging = staging_buf.view(world, self.shard_rows, self.stride)
+        self.peer_records, self.peer_staging = list(peer_records), list(peer_staging)
+        self.exp_avg = torch.zeros((self.shard_rows, self.stride), dtype=torch.float32, device=records_buf.device)
+        self.exp_avg_sq = torch.zeros_like(self.exp_avg)
+        self._barrier = barrier
+
+    def barrier(self):
+        """Device-side barrier over the ranks, ordered on the current stream (no host block)."""
+        self._barrier()
+
+    def my_rows(self):
+        b = self.rank * self.shard_rows
+        return b, max(0, min(self.shard_rows, self.N - b))
+
+    @staticmethod
+    def create(D: int, N: int, group=None, device=None) -> "ShardedState":
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from .fused import record_stride
+
+        group = dist.group.WORLD if group is None else group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        S, stride = shard_rows_for(N, world), record_stride(D)
+        rec = symm_mem.empty((world * S * stride,), dtype=torch.float32, device=device)
+        stg = symm_mem.empty((world * S * stride,), dtype=torch.float32, device=device)
+        rec.zero_()
+        stg.zero_()  # the padding rows of a shard are never written and must read as zero gradient
+        h_rec, h_stg = symm_mem.rendezvous(rec, group), symm_mem.rendezvous(stg, group)
+        st = ShardedState(D, N, world, rank, rec, stg, h_rec.buffer_ptrs, h_stg.buffer_ptrs,
+                          lambda: h_rec.barrier(channel=0))
+        st._handles = (h_rec, h_stg)
+        st.barrier()
+        return st
+
+    @staticmethod
+    def create_local_group(D: int, N: int, world: int, device="cuda"):
+        from .fused import record_stride
+
+        S, stride = shard_rows_for(N, world), record_stride(D)
+        recs = [torch.zeros((world * S * stride,), dtype=torch.float32, device=device) for _ in range(world)]
+        stgs = [torch.zeros((world * S * stride,), dtype=torch.float32, device=device) for _ in range(world)]
+        return [ShardedState(D, N, world, r, recs[r], stgs[r], [t.data_ptr() for t in recs],
+                             [t.data_ptr() for t in stgs], lambda: None) for r in range(world)]
+
+
+def shard_rows_for(N: int, world: int, align: int = 128) -> int:
+    per = -(-max(N, 1) // world)
+    return -(-per // align) * align
+
+
+@torch.no_grad()
+def sharded_backward_scatter(rz, st: ShardedState, viewmats, Ks, cam_pos, timestamps):
+    """Projection backward of the most recent composite_backward(): gradient tiles into the owners' staging slots."""
+    import ctypes
+
+    from ._lib import check, ptr
+
+    assert rz.C == 1 and rz.N == st.N
+    arr = (ctypes.c_void_p * st.world)(*st.peer_staging)
+    check(rz.lib.ubs_fused_project_bwd_scatter(
+        st.N, st.D, ptr(st.records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), rz.W, rz.H, rz.eps2d,
+        1 if rz.aa else 0, ptr(rz.radii), ptr(rz.conics), ptr(rz.v_means2d), None, ptr(rz.v_conics),
+        ptr(rz.v_opacities), ptr(rz.v_betas), ptr(rz.v_colors), st.world, st.rank, st.shard_rows,
+        ctypes.cast(arr, ctypes.c_void_p), torch.cuda.current_stream().cuda_stream), "ubs_fused_project_bwd_scatter")
+
+
+@torch.no_grad()
+def sharded_reduce_adam_gather(st: ShardedState, adam, opacity_reg: float = 0.0, scale_reg: float = 0.0,
+                               advance: bool = True):
+    """Owner side: sum the staging slots, Adam on the shard, new parameters into every rank's records.
+    `adam` supplies learning rates, betas, eps and the step count (a training.PackedAdam; its own moment buffers
+    are not used -- the shard's live in `st`)."""
+    import ctypes
+
+    from ._lib import check, ptr
+
+    if advance:
+        adam.step_count += 1
+    cols = (ctypes.c_double * st.stride)(*adam.lr_columns())
+    arr = (ctypes.c_void_p * st.world)(*st.peer_records)
+    check(adam.lib.ubs_reduce_adam_gather(
+        st.N, st.D, st.world, st.rank, st.shard_rows, ptr(st.staging), ptr(st.exp_avg), ptr(st.exp_avg_sq),
+        ctypes.cast(arr, ctypes.c_void_p), ctypes.cast(cols, ctypes.c_void_p), adam.betas[0], adam.betas[1], adam.eps,
+        adam.step_count, float(opacity_reg), float(scale_reg), torch.cuda.current_stream().cuda_stream),
+        "ubs_reduce_adam_gather")
+
+
 class DataParallelTrainer:
     """forward + backward of one view per rank with the (chunk-pipelined) gradient all-reduce.
     `rz` is a fused.FusedRasterizer."""

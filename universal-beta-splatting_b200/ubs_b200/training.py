@@ -128,7 +128,7 @@ class PackedAdam:
     GROUPS = ("xyz", "mean", "rgb", "opacity", "beta", "scale", "l_triangle")
 
     def __init__(self, D: int, N: int, lr: Optional[Dict[str, float]] = None, betas=(0.9, 0.999), eps: float = 1e-15,
-                 device="cuda"):
+                 device="cuda", allocate_moments: bool = True):
         self.lib = _lib.load()
         self.D, self.N = D, N
         self.stride = record_stride(D)
@@ -136,8 +136,11 @@ class PackedAdam:
         assert set(self.lr) == set(self.GROUPS), "one learning rate per parameter group: %s" % (self.GROUPS,)
         self.betas, self.eps = betas, eps
         self.step_count = 0
-        self.exp_avg = torch.zeros((N, self.stride), dtype=torch.float32, device=device)
-        self.exp_avg_sq = torch.zeros((N, self.stride), dtype=torch.float32, device=device)
+        # allocate_moments=False: hyper-parameters and step count only (the sharded step keeps each rank's moment
+        # shard in parallel.ShardedState)
+        rows = N if allocate_moments else 0
+        self.exp_avg = torch.zeros((rows, self.stride), dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros((rows, self.stride), dtype=torch.float32, device=device)
 
     def set_lr(self, group: str, value: float):
         assert group in self.lr
@@ -223,9 +226,13 @@ class TrainStep:
     forward -> L1+SSIM loss and its image gradient -> backward -> (all-reduce) -> Adam.  Zero host syncs."""
 
     def __init__(self, rz: FusedRasterizer, adam: PackedAdam, lambda_dssim: float = 0.2, world: int = 1, group=None,
-                 fuse_adam: bool = True, n_chunks: int = 4):
+                 fuse_adam: bool = True, n_chunks: int = 4, sharded=None):
         assert rz.C == 1
         self.n_chunks = n_chunks
+        # sharded: a parallel.ShardedState -- gradient tiles go over NVLink into the owner rank's staging buffer
+        # straight from the projection-backward kernel, the owner reduces + applies Adam to its 1/world of the rows
+        # and stores the new parameters into every rank's records; `records` passed to step() must be sharded.records
+        self.sharded = sharded
         self.rz, self.adam, self.lam, self.world, self.group = rz, adam, lambda_dssim, world, group
         # one view per optimiser step on one GPU (the reference's default batch_size = 1): nothing to sum before the
         # update, so Adam rides in the projection-backward kernel and the gradient records never reach HBM
@@ -242,8 +249,9 @@ class TrainStep:
         from . import parallel
 
         rz = self.rz
-        fused_update = self.fuse_adam and self.world == 1
-        if not fused_update and (self.v_records is None or self.v_records.shape != records.shape):
+        fused_update = self.fuse_adam and self.world == 1 and self.sharded is None
+        if not fused_update and self.sharded is None and (self.v_records is None or
+                                                          self.v_records.shape != records.shape):
             self.v_records = torch.empty_like(records)
         rc, _ = rz.forward(records, viewmats, Ks, cam_pos, timestamps, backgrounds)
         if gt.dim() == 3:
@@ -253,6 +261,19 @@ class TrainStep:
         if fused_update:
             rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, self.v_rc, self.v_ra, None, self.adam,
                         opacity_reg, scale_reg)
+            return self.loss_out
+        if self.sharded is not None:
+            st = self.sharded
+            assert records.data_ptr() == st.records.data_ptr(), "step() must be given ShardedState.records"
+            rz.composite_backward(backgrounds, self.v_rc, self.v_ra)
+            with rz._stage("bwd_scatter"):
+                parallel.sharded_backward_scatter(rz, st, viewmats, Ks, cam_pos, timestamps)
+            with rz._stage("barrier"):
+                st.barrier()  # every rank's contribution to my shard has landed
+            with rz._stage("reduce_adam_gather"):
+                parallel.sharded_reduce_adam_gather(st, self.adam, opacity_reg, scale_reg)
+            with rz._stage("barrier"):
+                st.barrier()  # every shard's new parameters have landed in my records
             return self.loss_out
         # world > 1: the projection backward runs chunk by chunk; chunk k's gradient all-reduce (NCCL, its own stream)
         # overlaps the backward of chunk k+1 and the Adam update of chunk k-1
