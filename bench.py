@@ -22,8 +22,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "universal-beta-splatting_b200"))
 sys.path.insert(0, ROOT)
 
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries the ONE JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    # at these two levels NCCL prints its version banner to stdout, which carries the ONE JSON line; INFO and above
+    # (e.g. when someone wants the NVLS evidence) are left alone
+    os.environ["NCCL_DEBUG"] = "NONE"
 # the gradient all-reduce is pipelined against the projection backward / Adam kernels (parallel.pipelined_backward);
 # NCCL's kernels only get SMs next to those full-machine grids from a high-priority stream (measured at 2 GPUs)
 os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
@@ -326,7 +328,16 @@ def run_ours(args, rank, local_rank, world):
 
     rec_train = rec.clone()  # Adam moves the parameters: keep the render workload's records untouched
     gt_img = torch.rand(1, 3, H, W, device=dev, generator=g)
-    tstep = training.TrainStep(rz, training.PackedAdam(D, N, device=dev), world=world)
+    sharded = None
+    if world > 1:
+        # rows sharded over the ranks: gradient tiles go over NVLink into the owner's staging buffer from inside the
+        # projection-backward kernel, the owner reduces + applies Adam and stores the new rows into every rank
+        sharded = parallel.ShardedState.create(D, N)
+        sharded.records.copy_(rec)
+        del rec_train
+        rec_train = sharded.records
+    tstep = training.TrainStep(rz, training.PackedAdam(D, N, device=dev, allocate_moments=sharded is None), world=world,
+                               sharded=sharded)
 
     def train_full(step):
         c = cam_of(step)
@@ -335,7 +346,16 @@ def run_ours(args, rank, local_rank, world):
 
     ms_full, launches_full, clocks_full, stages_full = timed(train_full, args.steps, args.warmup, True)
     its_full = world * args.steps / (ms_full / 1e3)
-    del rec_train, tstep
+    del rec_train, tstep, sharded
+    nccl_full = None
+    if world > 1:
+        # the same step through NCCL: chunk-pipelined all-reduce of the gradient records + Adam on every rank
+        rec_train = rec.clone()
+        tstep = training.TrainStep(rz, training.PackedAdam(D, N, device=dev), world=world)
+        ms_n, _, _, st_n = timed(train_full, args.steps, args.warmup, True)
+        nccl_full = {"value": world * args.steps / (ms_n / 1e3), "unit": "it/s", "ms_per_step": ms_n / args.steps,
+                     "stages_ms": {k: v[1] for k, v in st_n.items()}}
+        del rec_train, tstep
 
     # ---- e2e: host buffers in, host image out, through the public API -----------------------------------------
     h_cam = torch.empty((N_RING, 16 + 9 + 3 + 1), dtype=torch.float32).pin_memory()
@@ -478,7 +498,12 @@ def run_ours(args, rank, local_rank, world):
                                "projection-backward kernel at 1 GPU, a separate pass after the all-reduce otherwise) "
                                "(train.py:100-171 for one view per GPU)",
                        "gpu_launches": launches_full, "clocks": clocks_full,
-                       "stages_ms": {k: v[1] for k, v in stages_full.items()}},
+                       "stages_ms": {k: v[1] for k, v in stages_full.items()},
+                       "update": ("Adam inside the projection-backward kernel" if world == 1 else
+                                  "rows sharded over the ranks: NVLink peer stores from the projection-backward "
+                                  "kernel into the owner's staging buffer, owner-side reduce + Adam + parameter "
+                                  "stores to every rank (symmetric memory)"),
+                       "nccl_allreduce_path": nccl_full},
         "roofline": roofline, "stages": stage_roof, "stages_ms": {k: v[1] for k, v in stages.items()},
         "work": counts, "cpu_baseline": cpu,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
