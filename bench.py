@@ -384,7 +384,7 @@ def run_ours(args, rank, local_rank, world):
         t_e2e = t.item()
     e2e_fps = world * args.steps / t_e2e
     h2d = h_cam[0].numel() * 4
-    d2h = P * 4 * 4
+    d2h = P * 3 * 4  # the FP32 RGB image (what BetaModel.view returns to the host)
 
     if rank != 0:
         if world > 1:
@@ -507,7 +507,7 @@ def run_ours(args, rank, local_rank, world):
         "roofline": roofline, "stages": stage_roof, "stages_ms": {k: v[1] for k, v in stages.items()},
         "work": counts, "cpu_baseline": cpu,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "what": "fused.HostPipeline.render_to_host: pinned host camera -> device, render, RGBA image -> "
+                "what": "fused.HostPipeline.render_to_host: pinned host camera -> device, render, FP32 RGB image -> "
                         "pinned host, double-buffered; wall clock over the timed steps"},
         "gpu_launches": launches, "clocks": clocks,
     }

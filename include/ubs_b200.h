@@ -303,6 +303,8 @@ int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *records, const 
                                   int rank, int64_t shard_rows, float *const *h_staging, void *stream);
 int ubs_reduce_adam_gather(int64_t N, int D, int world, int rank, int64_t shard_rows, const float *staging,
                            float *exp_avg_shard, float *exp_avg_sq_shard, float *const *h_peer_records,
+                           float *mc_records, /* NULL, or the NVLS multicast address of the records buffers: one
+                                                 multimem.st per element instead of `world` peer stores */
                            const double *h_lr, double beta1, double beta2, double eps, int64_t step,
                            double opacity_reg, double scale_reg, void *stream);
 

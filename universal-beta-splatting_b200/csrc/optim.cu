@@ -50,7 +50,8 @@ struct PeerRecords {
 __global__ void __launch_bounds__(256)
 reduce_adam_gather_kernel(int64_t n_vec, int vec_per_row, int64_t row_begin, int world, int64_t slot_vecs,
                           const float4 *__restrict__ staging, float4 *__restrict__ exp_avg,
-                          float4 *__restrict__ exp_avg_sq, PeerRecords peers, int rank, AdamParams a) {
+                          float4 *__restrict__ exp_avg_sq, PeerRecords peers, float4 *__restrict__ mc_records,
+                          int rank, AdamParams a) {
     __shared__ float s_step[kAdamMaxStride];
     if (threadIdx.x < kAdamMaxStride) s_step[threadIdx.x] = a.step_size[threadIdx.x];
     __syncthreads();
@@ -74,7 +75,15 @@ reduce_adam_gather_kernel(int64_t n_vec, int vec_per_row, int64_t row_begin, int
         exp_avg[i] = make_float4(m[0], m[1], m[2], m[3]);
         exp_avg_sq[i] = make_float4(v[0], v[1], v[2], v[3]);
         const float4 out = make_float4(p[0], p[1], p[2], p[3]);
-        for (int j = 0; j < world; ++j) peers.p[j][rec_off + i] = out;
+        if (mc_records != nullptr) {
+            // one store to the multicast address: the NVSwitch replicates it into every rank's records (this rank's
+            // included), so the owner's link carries its shard once instead of world - 1 times
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_records + rec_off + i),
+                         "f"(out.x), "f"(out.y), "f"(out.z), "f"(out.w)
+                         : "memory");
+        } else {
+            for (int j = 0; j < world; ++j) peers.p[j][rec_off + i] = out;
+        }
     }
 }
 
@@ -182,7 +191,7 @@ extern "C" int ubs_mcmc_relocate(int64_t N, int D, float *records, float *exp_av
 
 extern "C" int ubs_reduce_adam_gather(int64_t N, int D, int world, int rank, int64_t shard_rows, const float *staging,
                                       float *exp_avg_shard, float *exp_avg_sq_shard, float *const *h_peer_records,
-                                      const double *h_lr, double beta1, double beta2, double eps, int64_t step,
+                                      float *mc_records, const double *h_lr, double beta1, double beta2, double eps, int64_t step,
                                       double opacity_reg, double scale_reg, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(N >= 0 && D >= 4 && D <= 8, "reduce_adam_gather: bad sizes (N=%lld, D=%d)", (long long)N, D);
@@ -213,7 +222,7 @@ extern "C" int ubs_reduce_adam_gather(int64_t N, int D, int world, int rank, int
     const unsigned grid = (unsigned)(blocks < (int64_t)sm * 16 ? blocks : (int64_t)sm * 16);
     reduce_adam_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         n_vec, stride / 4, row_begin, world, shard_rows * (stride / 4), (const float4 *)staging, (float4 *)exp_avg_shard,
-        (float4 *)exp_avg_sq_shard, peers, rank, a);
+        (float4 *)exp_avg_sq_shard, peers, (float4 *)mc_records, rank, a);
     UBS_LAUNCH_CHECK("reduce_adam_gather_kernel");
     return UBS_OK;
 }

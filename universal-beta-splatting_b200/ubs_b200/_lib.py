@@ -56,7 +56,7 @@ SIGNATURES = {
                                    [_P] * 11 + [c_double, c_double, c_double, c_int64, c_double, c_double, _P]),
     "ubs_fused_project_bwd_scatter": (c_int, [c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_int] +
                                       [_P] * 8 + [c_int, c_int, c_int64, _P, _P]),
-    "ubs_reduce_adam_gather": (c_int, [c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P, _P, _P, c_double, c_double,
+    "ubs_reduce_adam_gather": (c_int, [c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P, c_double, c_double,
                                        c_double, c_int64, c_double, c_double, _P]),
     "ubs_mcmc_relocate": (c_int, [c_int64, c_int, _P, _P, _P, c_int64, _P, _P, _P, _P]),
 }

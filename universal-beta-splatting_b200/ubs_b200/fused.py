@@ -296,8 +296,10 @@ class HostPipeline:
 
     CAM_FLOATS = 29
 
-    def __init__(self, rz: "FusedRasterizer", depth: int = 2):
-        self.rz, self.depth = rz, depth
+    def __init__(self, rz: "FusedRasterizer", depth: int = 2, copy_alpha: bool = False):
+        # copy_alpha=False: the host gets what BetaModel.view / Scene.eval hand back -- the colour image
+        # (scene/beta_model.py:827-831); the alpha plane stays on the device unless asked for
+        self.rz, self.depth, self.copy_alpha = rz, depth, copy_alpha
         dev, C, H, W = rz.device, rz.C, rz.H, rz.W
         assert C == 1, "HostPipeline renders one camera per frame"
         self.cam_dev = [torch.empty((self.CAM_FLOATS,), dtype=torch.float32, device=dev) for _ in range(depth)]
@@ -326,7 +328,8 @@ class HostPipeline:
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(done)
             self.img_host[slot][0].copy_(rc, non_blocking=True)
-            self.img_host[slot][1].copy_(ra, non_blocking=True)
+            if self.copy_alpha:
+                self.img_host[slot][1].copy_(ra, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         self.copied[slot] = ev
