@@ -64,7 +64,11 @@ def _random_splats(C, N, W, H, seed, rmax=40, tie_frac=0.0, depth_lo=0.5, depth_
 @pytest.mark.parametrize("C,N,W,H,rmax,tie", [(1, 30000, 640, 480, 40, 0.0), (1, 30000, 640, 480, 40, 0.5),
                                                (3, 9000, 200, 136, 30, 0.2), (1, 500, 1920, 1080, 20, 0.0),
                                                (2, 4000, 64, 48, 200, 0.3),   # every tile far above kSegMax
-                                               (1, 3000, 96, 96, 60, 1.0)])   # all depths from a pool of 7
+                                               (1, 3000, 96, 96, 60, 1.0),    # all depths from a pool of 7
+                                               # tiles of 2049..4096 / 4097..8192 pairs (the 16- and 32-pairs-per-thread
+                                               # shared-memory sorts) mixed with shorter and longer ones
+                                               (1, 40000, 320, 240, 50, 0.0), (1, 60000, 320, 240, 60, 0.3),
+                                               (2, 25000, 400, 300, 70, 0.1)])
 def test_bin_sort_matches_stable_sort_definition(C, N, W, H, rmax, tie):
     from ubs_b200 import ops
 

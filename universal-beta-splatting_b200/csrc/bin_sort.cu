@@ -29,8 +29,10 @@ namespace {
 
 constexpr int kSegThreads = 256;
 constexpr int kSegWarps = kSegThreads / 32;
-constexpr int kSegItems = 8;                       // elements per thread in the shared-memory sort
-constexpr int kSegMax = kSegThreads * kSegItems;   // longest segment sorted in shared memory
+constexpr int kSegItems = 8;                       // elements per thread in the shared-memory sort (short segments)
+constexpr int kSegMax = kSegThreads * kSegItems;   // longest segment of the first shared-memory instantiation
+constexpr int kSegItemsMid = 16, kSegItemsLong = 32;                 // 2049..4096 and 4097..8192 pairs per tile
+constexpr int kSegMaxShared = kSegThreads * kSegItemsLong;          // beyond this: segment_sort_big_kernel
 constexpr int kScanThreads = 1024;
 // Atomic targets are spread to one per 32-byte sector: with 4-byte spacing the whole cursor array sits in a few
 // L2 slices and one slice's atomic unit saturates (lts__d_atomic_input_cycles_active: max 65 %, mean 8.5 %).
@@ -340,15 +342,16 @@ __device__ __forceinline__ uint32_t warp_rank_digit(uint32_t d, bool valid, uint
 //   * per-warp digit counters -> (thread per digit, or per digit pair when BITS == 9) exclusive offsets over warps,
 //     one block scan, segment-wide digit bases folded back into the per-warp counters, so the scatter position is
 //     one shared load + the in-warp rank.
+template <int ITEMS>
 struct SegSmem {
-    unsigned long long kv[2][kSegMax];       // 32 KB
+    unsigned long long kv[2][kSegThreads * ITEMS];  // 32 / 64 / 128 KB
     __align__(16) uint32_t cnt[kSegWarps * 512];  // 16 KB
     uint32_t tmp[kSegWarps];
     uint32_t wmin[kSegWarps], wmax[kSegWarps];
 };
 
-template <int BITS>
-__device__ __noinline__ void segment_radix_pass(SegSmem &sm, int cur, int shift, int32_t n, int32_t chunk) {
+template <int BITS, int ITEMS>
+__device__ __noinline__ void segment_radix_pass(SegSmem<ITEMS> &sm, int cur, int shift, int32_t n, int32_t chunk) {
     constexpr int NDIG = 1 << BITS;
     constexpr int PER = NDIG > kSegThreads ? NDIG / kSegThreads : 1;  // digits per thread in the prefix step
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -357,11 +360,11 @@ __device__ __noinline__ void segment_radix_pass(SegSmem &sm, int cur, int shift,
     __syncthreads();
     uint32_t *my_cnt = sm.cnt + warp * NDIG;
     const int32_t wbase = (int32_t)warp * chunk;
-    uint32_t rank2[kSegItems / 2];  // two 16-bit in-warp ranks per register (a rank is < kSegMax)
+    uint32_t rank2[ITEMS / 2];  // two 16-bit in-warp ranks per register (a rank is < kSegMax)
 #pragma unroll
-    for (int it = 0; it < kSegItems / 2; ++it) rank2[it] = 0;
+    for (int it = 0; it < ITEMS / 2; ++it) rank2[it] = 0;
 #pragma unroll
-    for (int it = 0; it < kSegItems; ++it) {
+    for (int it = 0; it < ITEMS; ++it) {
         if (it * 32 < chunk) {
             const int32_t e = wbase + it * 32 + (int32_t)lane;
             const bool valid = e < n;
@@ -415,7 +418,7 @@ __device__ __noinline__ void segment_radix_pass(SegSmem &sm, int cur, int shift,
     }
     __syncthreads();
 #pragma unroll
-    for (int it = 0; it < kSegItems; ++it) {
+    for (int it = 0; it < ITEMS; ++it) {
         if (it * 32 < chunk) {
             const int32_t e = wbase + it * 32 + (int32_t)lane;
             if (e < n) {
@@ -428,25 +431,21 @@ __device__ __noinline__ void segment_radix_pass(SegSmem &sm, int cur, int shift,
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSegThreads, 4)
-segment_sort_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits, const int32_t *__restrict__ offsets,
-                    const int64_t *__restrict__ n_isects_dev, int64_t capacity, const uint64_t *__restrict__ keyval,
-                    int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
-    extern __shared__ __align__(16) unsigned char seg_smem_raw[];
-    SegSmem &sm = *reinterpret_cast<SegSmem *>(seg_smem_raw);
-
-    const int64_t n_total = min(*n_isects_dev, capacity);
-    const SegRange seg = segment_of(blockIdx.x, n_slots, n_tiles, tile_n_bits, offsets, n_total);
+// Sort of one tile's segment in shared memory (all threads of the CTA; ends with the sorted pairs written out).
+// ITEMS pairs per thread: 8 (tiles of up to 2048 pairs), 16 (up to 4096), 32 (up to 8192).
+template <int ITEMS>
+__device__ __forceinline__ void sort_segment_shared(SegSmem<ITEMS> &sm, const SegRange seg,
+                                                    const uint64_t *__restrict__ keyval,
+                                                    int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
     const int32_t n = seg.n;
-    if (n <= 0 || n > kSegMax) return;  // long segments: segment_sort_big_kernel
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t *src = keyval + seg.start;
 
     // ---- depth range of the segment; keys are stored relative to the smallest one ------------------------------
-    unsigned long long mine[kSegItems];
+    unsigned long long mine[ITEMS];
     uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
-    for (int it = 0; it < kSegItems; ++it) {
+    for (int it = 0; it < ITEMS; ++it) {
         const int32_t i = it * kSegThreads + (int32_t)tid;
         if (i < n) {
             mine[it] = src[i];
@@ -469,7 +468,7 @@ segment_sort_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits, co
     }
     const uint32_t lo = kmin;
 #pragma unroll
-    for (int it = 0; it < kSegItems; ++it) {
+    for (int it = 0; it < ITEMS; ++it) {
         const int32_t i = it * kSegThreads + (int32_t)tid;
         if (i < n) sm.kv[0][i] = mine[it] - ((unsigned long long)lo << 32);
     }
@@ -484,15 +483,15 @@ segment_sort_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits, co
     for (int p = 0; p < passes; ++p) {
         const int shift = p * width;
         switch (width) {  // uniform across the CTA
-            case 1: segment_radix_pass<1>(sm, cur, shift, n, chunk); break;
-            case 2: segment_radix_pass<2>(sm, cur, shift, n, chunk); break;
-            case 3: segment_radix_pass<3>(sm, cur, shift, n, chunk); break;
-            case 4: segment_radix_pass<4>(sm, cur, shift, n, chunk); break;
-            case 5: segment_radix_pass<5>(sm, cur, shift, n, chunk); break;
-            case 6: segment_radix_pass<6>(sm, cur, shift, n, chunk); break;
-            case 7: segment_radix_pass<7>(sm, cur, shift, n, chunk); break;
-            case 8: segment_radix_pass<8>(sm, cur, shift, n, chunk); break;
-            default: segment_radix_pass<9>(sm, cur, shift, n, chunk); break;
+            case 1: segment_radix_pass<1, ITEMS>(sm, cur, shift, n, chunk); break;
+            case 2: segment_radix_pass<2, ITEMS>(sm, cur, shift, n, chunk); break;
+            case 3: segment_radix_pass<3, ITEMS>(sm, cur, shift, n, chunk); break;
+            case 4: segment_radix_pass<4, ITEMS>(sm, cur, shift, n, chunk); break;
+            case 5: segment_radix_pass<5, ITEMS>(sm, cur, shift, n, chunk); break;
+            case 6: segment_radix_pass<6, ITEMS>(sm, cur, shift, n, chunk); break;
+            case 7: segment_radix_pass<7, ITEMS>(sm, cur, shift, n, chunk); break;
+            case 8: segment_radix_pass<8, ITEMS>(sm, cur, shift, n, chunk); break;
+            default: segment_radix_pass<9, ITEMS>(sm, cur, shift, n, chunk); break;
         }
         cur ^= 1;
     }
@@ -515,7 +514,56 @@ segment_sort_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits, co
     }
 }
 
-// Long segments (n > kSegMax): LSD radix sort of the full 64-bit words (depth_bits << 32 | id: unique, so no tie
+// Short segments (the common case): one CTA per tile, 4 CTAs per SM.
+__global__ void __launch_bounds__(kSegThreads, 4)
+segment_sort_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits, const int32_t *__restrict__ offsets,
+                    const int64_t *__restrict__ n_isects_dev, int64_t capacity, const uint64_t *__restrict__ keyval,
+                    int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
+    extern __shared__ __align__(16) unsigned char seg_smem_raw[];
+    SegSmem<kSegItems> &sm = *reinterpret_cast<SegSmem<kSegItems> *>(seg_smem_raw);
+    const int64_t n_total = min(*n_isects_dev, capacity);
+    const SegRange seg = segment_of(blockIdx.x, n_slots, n_tiles, tile_n_bits, offsets, n_total);
+    if (seg.n <= 0 || seg.n > kSegMax) return;  // longer segments: segment_sort_long_kernel / segment_sort_big_kernel
+    sort_segment_shared<kSegItems>(sm, seg, keyval, isect_ids, flatten_ids);
+}
+
+// Tiles with 2049..4096 (ITEMS = 16) or 4097..8192 (ITEMS = 32) pairs -- dense regions, coarse tile grids: the same
+// shared-memory sort with more pairs per thread.  A persistent grid: every CTA owns a contiguous range of slots,
+// finds the ones of its length class with all threads in parallel and sorts them one after the other (a grid of one
+// CTA per slot would spend its time launching CTAs that exit: few tiles are this long).
+template <int ITEMS>
+__global__ void __launch_bounds__(kSegThreads, ITEMS == 16 ? 2 : 1)
+segment_sort_long_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits, const int32_t *__restrict__ offsets,
+                         const int64_t *__restrict__ n_isects_dev, int64_t capacity,
+                         const uint64_t *__restrict__ keyval, int64_t *__restrict__ isect_ids,
+                         int32_t *__restrict__ flatten_ids) {
+    extern __shared__ __align__(16) unsigned char seg_smem_raw[];
+    SegSmem<ITEMS> &sm = *reinterpret_cast<SegSmem<ITEMS> *>(seg_smem_raw);
+    constexpr int kMaxN = kSegThreads * ITEMS, kMinN = kMaxN / 2;
+    __shared__ uint32_t s_long[kSegThreads];
+    __shared__ uint32_t s_n_long;
+    const uint32_t tid = threadIdx.x;
+    const int64_t n_total = min(*n_isects_dev, capacity);
+    const uint32_t per_cta = (n_slots + gridDim.x - 1) / gridDim.x;
+    const uint32_t slot_begin = blockIdx.x * per_cta, slot_end = min(n_slots, slot_begin + per_cta);
+    for (uint32_t s0 = slot_begin; s0 < slot_end; s0 += kSegThreads) {
+        if (tid == 0) s_n_long = 0;
+        __syncthreads();
+        if (s0 + tid < slot_end) {
+            const int32_t n = segment_of(s0 + tid, n_slots, n_tiles, tile_n_bits, offsets, n_total).n;
+            if (n > kMinN && n <= kMaxN) s_long[atomicAdd(&s_n_long, 1u)] = s0 + tid;
+        }
+        __syncthreads();
+        const uint32_t n_long = s_n_long;
+        for (uint32_t li = 0; li < n_long; ++li) {
+            const SegRange seg = segment_of(s_long[li], n_slots, n_tiles, tile_n_bits, offsets, n_total);
+            sort_segment_shared<ITEMS>(sm, seg, keyval, isect_ids, flatten_ids);
+            __syncthreads();  // the next segment reuses the shared buffers
+        }
+    }
+}
+
+// Long segments (n > kSegMaxShared = 8192): LSD radix sort of the full 64-bit words (depth_bits << 32 | id: unique, so no tie
 // pass) in global memory, ping-ponging between the segment's span of `keyval` and of `alt`.  One CTA per segment,
 // found by striding over the slots; correctness for any length matters here, speed does not.
 __global__ void __launch_bounds__(kSegThreads)
@@ -536,7 +584,7 @@ segment_sort_big_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits
     for (uint32_t s0 = slot_begin; s0 < slot_end; s0 += kSegThreads) {
       if (tid == 0) s_n_long = 0;
       __syncthreads();
-      if (s0 + tid < slot_end && segment_of(s0 + tid, n_slots, n_tiles, tile_n_bits, offsets, n_total).n > kSegMax)
+      if (s0 + tid < slot_end && segment_of(s0 + tid, n_slots, n_tiles, tile_n_bits, offsets, n_total).n > kSegMaxShared)
           s_long[atomicAdd(&s_n_long, 1u)] = s0 + tid;
       __syncthreads();
       const uint32_t n_long = s_n_long;
@@ -682,17 +730,33 @@ extern "C" int ubs_isect_bin_sort(int C, int64_t N, const float *means2d, const 
         CN, N, means2d, radii, depths, (uint32_t)tile_size, (uint32_t)tile_width, (uint32_t)tile_height, capacity,
         w.cursor, w.keyval);
     UBS_LAUNCH_CHECK("bin_emit_kernel");
+    int sm = ubs_device_sm_count();
+    if (sm <= 0) sm = 148;
     static bool seg_attr_set = false;
     if (!seg_attr_set) {
         UBS_CUDA_TRY(cudaFuncSetAttribute(segment_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(SegSmem)));
+                                          (int)sizeof(SegSmem<kSegItems>)));
+        UBS_CUDA_TRY(cudaFuncSetAttribute(segment_sort_long_kernel<kSegItemsMid>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SegSmem<kSegItemsMid>)));
+        UBS_CUDA_TRY(cudaFuncSetAttribute(segment_sort_long_kernel<kSegItemsLong>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SegSmem<kSegItemsLong>)));
         seg_attr_set = true;
     }
-    segment_sort_kernel<<<n_slots, kSegThreads, sizeof(SegSmem), s>>>(n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects,
-                                                        capacity, w.keyval, isect_ids, flatten_ids);
+    segment_sort_kernel<<<n_slots, kSegThreads, sizeof(SegSmem<kSegItems>), s>>>(
+        n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects, capacity, w.keyval, isect_ids, flatten_ids);
     UBS_LAUNCH_CHECK("segment_sort_kernel");
-    int sm = ubs_device_sm_count();
-    if (sm <= 0) sm = 148;
+    if (capacity > kSegMax) {  // a tile of more than 2048 pairs is possible at all
+        const unsigned g_mid = n_slots < (unsigned)(2 * sm) ? n_slots : (unsigned)(2 * sm);
+        segment_sort_long_kernel<kSegItemsMid><<<g_mid, kSegThreads, sizeof(SegSmem<kSegItemsMid>), s>>>(
+            n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects, capacity, w.keyval, isect_ids, flatten_ids);
+        UBS_LAUNCH_CHECK("segment_sort_long_kernel");
+        const unsigned g_long = n_slots < (unsigned)sm ? n_slots : (unsigned)sm;
+        segment_sort_long_kernel<kSegItemsLong><<<g_long, kSegThreads, sizeof(SegSmem<kSegItemsLong>), s>>>(
+            n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects, capacity, w.keyval, isect_ids, flatten_ids);
+        UBS_LAUNCH_CHECK("segment_sort_long_kernel");
+    }
     const unsigned big_grid = n_slots < (unsigned)(2 * sm) ? n_slots : (unsigned)(2 * sm);
     segment_sort_big_kernel<<<big_grid, kSegThreads, 0, s>>>(n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects,
                                                              capacity, w.keyval, w.alt, isect_ids, flatten_ids);
