@@ -74,4 +74,36 @@ __device__ __forceinline__ uint32_t sub_tile_mask(float4 bb, float tx0, float ty
     if (bb.z <= ty0 + 15.f && bb.w >= ty0 + 12.f) my |= 0xC0u;
     return mx & my;
 }
+
+// Refinement of sub_tile_mask for the backward pass (where a (warp, pair) evaluation costs ~120 instructions): drop the
+// sub-tiles whose rectangle of pixel centres the ellipse {sigma < 1} misses although its bounding box overlaps them
+// (corners, thin tilted ellipses).  Exact minimum of the convex quadratic sigma over the rectangle: when the centre is
+// outside, the minimiser lies on an edge facing the centre, so at most two clamped 1-D minimisations are needed.
+// Conservative by a margin far above rounding: a sub-tile is only dropped when min sigma >= 1.001.
+__device__ __forceinline__ uint32_t refine_sub_tile_mask(uint32_t mask, float mx, float my, float a, float b, float c,
+                                                         float tx0, float ty0) {
+    if (!(a > 0.f && c > 0.f && a * c - b * b > 0.f)) return mask;  // degenerate conic: keep the box test
+    const float rc = 1.f / c, ra = 1.f / a;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        if (!((mask >> w) & 1u)) continue;
+        const float x0 = tx0 + (float)((w & 1) * kSubW), x1 = x0 + (float)(kSubW - 1);
+        const float y0 = ty0 + (float)((w >> 1) * kSubH), y1 = y0 + (float)(kSubH - 1);
+        const bool in_x = mx >= x0 && mx <= x1, in_y = my >= y0 && my <= y1;
+        if (in_x && in_y) continue;  // centre inside: sigma = 0 there
+        float qmin = 3.0e38f;
+        if (!in_x) {  // vertical edge facing the centre
+            const float dx = (mx < x0 ? x0 : x1) - mx;
+            const float dy = fminf(fmaxf(my - b * dx * rc, y0), y1) - my;
+            qmin = a * dx * dx + 2.f * b * dx * dy + c * dy * dy;
+        }
+        if (!in_y) {  // horizontal edge facing the centre
+            const float dy = (my < y0 ? y0 : y1) - my;
+            const float dx = fminf(fmaxf(mx - b * dy * ra, x0), x1) - mx;
+            qmin = fminf(qmin, a * dx * dx + 2.f * b * dx * dy + c * dy * dy);
+        }
+        if (qmin >= 1.001f) mask &= ~(1u << w);
+    }
+    return mask;
+}
 }  // namespace ubs

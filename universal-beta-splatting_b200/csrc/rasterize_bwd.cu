@@ -380,7 +380,8 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
             s_rec[tr].xyob = make_float4(xy.x, xy.y, opacities[g], betas[g]);
             s_rec[tr].conic = make_float4(ca, cb + cb, cc, 0.f);
             s_rec[tr].col = make_float4(colors[(size_t)g * 3], colors[(size_t)g * 3 + 1], colors[(size_t)g * 3 + 2], 0.f);
-            s_mask[tr] = (uint8_t)sub_tile_mask(support_bbox(xy.x, xy.y, ca, cb, cc), tx0, ty0);
+            s_mask[tr] = (uint8_t)refine_sub_tile_mask(sub_tile_mask(support_bbox(xy.x, xy.y, ca, cb, cc), tx0, ty0),
+                                                        xy.x, xy.y, ca, cb, cc, tx0, ty0);
         }
         __syncthreads();
 
