@@ -50,7 +50,7 @@ N_RING = 64
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -422,7 +422,7 @@ def run_ours(args, rank, local_rank, world):
     stage_kernels = {  # stage -> the kernels it launches (keys of profiles/traffic.json)
         "fused_project_fwd": ["fused_project_fwd_kernel"],
         "isect_emit_sort_offsets": ["bin_scan_kernel", "bin_emit_kernel", "segment_sort_kernel",
-                                    "segment_sort_big_kernel"],
+                                    "segment_sort_long_kernel"],
         "fused_project_bwd": ["fused_project_bwd_kernel"], "adam_step": ["adam_kernel"],
         "fused_project_bwd_adam": ["fused_project_bwd_adam_kernel"],
         "l1_ssim_loss": ["ssim_fwd_kernel", "loss_finalize_kernel", "ssim_bwd_kernel"],

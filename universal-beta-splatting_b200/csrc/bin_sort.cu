@@ -17,7 +17,8 @@
 //
 // HBM traffic per pair: 8 B written + 8 B read + 12 B written (the 50 MB segment buffer of a 3M-primitive frame
 // stays in the 126 MB L2) against 8 + 24 * 6 = 152 B for the six onesweep passes over 46-bit keys it replaces.
-// Segments longer than kSegMax are sorted by segment_sort_big_kernel in global memory (any length).
+// Segments longer than kSegMax (2048) are sorted by segment_sort_long_kernel: in shared memory up to 8192 pairs,
+// in global memory beyond (any length).
 //
 // Precondition: depths of visible primitives are >= +0 (near_plane > 0), so the reference's sign extension of the
 // depth bits (isect_tiles.cu:91) is the identity; callers with near_plane <= 0 use ubs_isect_emit_sort.
@@ -32,7 +33,7 @@ constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kSegItems = 8;                       // elements per thread in the shared-memory sort (short segments)
 constexpr int kSegMax = kSegThreads * kSegItems;   // longest segment of the first shared-memory instantiation
 constexpr int kSegItemsMid = 16, kSegItemsLong = 32;                 // 2049..4096 and 4097..8192 pairs per tile
-constexpr int kSegMaxShared = kSegThreads * kSegItemsLong;          // beyond this: segment_sort_big_kernel
+constexpr int kSegMaxShared = kSegThreads * kSegItemsLong;          // beyond this: sort_segment_global
 constexpr int kScanThreads = 1024;
 // Atomic targets are spread to one per 32-byte sector: with 4-byte spacing the whole cursor array sits in a few
 // L2 slices and one slice's atomic unit saturates (lts__d_atomic_input_cycles_active: max 65 %, mean 8.5 %).
@@ -523,23 +524,89 @@ segment_sort_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits, co
     SegSmem<kSegItems> &sm = *reinterpret_cast<SegSmem<kSegItems> *>(seg_smem_raw);
     const int64_t n_total = min(*n_isects_dev, capacity);
     const SegRange seg = segment_of(blockIdx.x, n_slots, n_tiles, tile_n_bits, offsets, n_total);
-    if (seg.n <= 0 || seg.n > kSegMax) return;  // longer segments: segment_sort_long_kernel / segment_sort_big_kernel
+    if (seg.n <= 0 || seg.n > kSegMax) return;  // longer segments: segment_sort_long_kernel
     sort_segment_shared<kSegItems>(sm, seg, keyval, isect_ids, flatten_ids);
 }
 
-// Tiles with 2049..4096 (ITEMS = 16) or 4097..8192 (ITEMS = 32) pairs -- dense regions, coarse tile grids: the same
-// shared-memory sort with more pairs per thread.  A persistent grid: every CTA owns a contiguous range of slots,
-// finds the ones of its length class with all threads in parallel and sorts them one after the other (a grid of one
-// CTA per slot would spend its time launching CTAs that exit: few tiles are this long).
-template <int ITEMS>
-__global__ void __launch_bounds__(kSegThreads, ITEMS == 16 ? 2 : 1)
+// Very long segments (n > kSegMaxShared = 8192): LSD radix sort of the full 64-bit words (depth_bits << 32 | id: unique,
+// so no tie pass) in global memory, ping-ponging between the segment's span of `keyval` and of `alt`.  Correct for
+// any length; speed matters little here.
+__device__ __noinline__ void sort_segment_global(const SegRange seg, uint64_t *keyval, uint64_t *alt,
+                                                 int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
+    __shared__ uint32_t s_cnt[kSegWarps * 256];
+    __shared__ uint32_t s_base[256];
+    __shared__ uint32_t s_tmp[kSegWarps];
+    __shared__ unsigned long long s_or[kSegWarps];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t n = seg.n;
+    uint64_t *src = keyval + seg.start, *dst = alt + seg.start;
+    // bits that differ anywhere in the segment
+    const uint64_t first = src[0];
+    unsigned long long diff = 0ull;
+    for (int32_t i = (int32_t)tid; i < n; i += kSegThreads) diff |= src[i] ^ first;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, off);
+    __syncthreads();
+    if (lane == 0) s_or[warp] = diff;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kSegWarps; ++w) diff |= s_or[w];
+
+    const int32_t chunk = (int32_t)(((int64_t)n + kSegThreads - 1) / kSegThreads) * 32;
+    const int32_t wbase = (int32_t)warp * chunk;
+    uint32_t *my_cnt = s_cnt + warp * 256;
+    for (int shift = 0; shift < 64; shift += 8) {
+        if (((diff >> shift) & 0xffull) == 0ull) continue;  // this digit is constant: the pass is the identity
+#pragma unroll
+        for (int k = 0; k < kSegWarps; ++k) s_cnt[k * 256 + tid] = 0;
+        __syncthreads();
+        for (int32_t e0 = wbase; e0 < wbase + chunk && e0 < n; e0 += 32) {
+            const int32_t e = e0 + (int32_t)lane;
+            const bool valid = e < n;
+            const uint32_t d = valid ? (uint32_t)((src[e] >> shift) & 0xffull) : 0u;
+            (void)warp_rank_digit(d, valid, my_cnt, lane);
+        }
+        __syncthreads();
+        uint32_t cnt_d = 0;
+#pragma unroll
+        for (int w = 0; w < kSegWarps; ++w) {
+            const uint32_t c = s_cnt[w * 256 + tid];
+            s_cnt[w * 256 + tid] = cnt_d;
+            cnt_d += c;
+        }
+        s_base[tid] = block_exclusive_scan_u32_256(cnt_d, s_tmp);
+        __syncthreads();
+        // second walk: the counters now run from each warp's exclusive offset
+        for (int32_t e0 = wbase; e0 < wbase + chunk && e0 < n; e0 += 32) {
+            const int32_t e = e0 + (int32_t)lane;
+            const bool valid = e < n;
+            const uint64_t kv = valid ? src[e] : 0ull;
+            const uint32_t d = valid ? (uint32_t)((kv >> shift) & 0xffull) : 0u;
+            const uint32_t r = warp_rank_digit(d, valid, my_cnt, lane);
+            if (valid) dst[s_base[d] + r] = kv;
+        }
+        __syncthreads();
+        uint64_t *t = src;
+        src = dst;
+        dst = t;
+    }
+    for (int32_t i = (int32_t)tid; i < n; i += kSegThreads) {
+        const uint64_t kv = src[i];
+        isect_ids[seg.start + i] = (int64_t)(seg.hi | (kv >> 32));
+        flatten_ids[seg.start + i] = (int32_t)(uint32_t)kv;
+    }
+    __syncthreads();
+}
+
+// Tiles with more than 2048 pairs -- dense regions, coarse tile grids -- in ONE launch: a persistent grid in which
+// every CTA owns a contiguous range of slots, finds its long ones with all threads in parallel and sorts them one
+// after the other: up to 4096 / 8192 pairs with the shared-memory sort at 16 / 32 pairs per thread, beyond that in
+// global memory.  (One CTA per slot would spend its time launching CTAs that exit: few tiles are this long.)
+__global__ void __launch_bounds__(kSegThreads, 1)
 segment_sort_long_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits, const int32_t *__restrict__ offsets,
-                         const int64_t *__restrict__ n_isects_dev, int64_t capacity,
-                         const uint64_t *__restrict__ keyval, int64_t *__restrict__ isect_ids,
-                         int32_t *__restrict__ flatten_ids) {
+                         const int64_t *__restrict__ n_isects_dev, int64_t capacity, uint64_t *keyval, uint64_t *alt,
+                         int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
     extern __shared__ __align__(16) unsigned char seg_smem_raw[];
-    SegSmem<ITEMS> &sm = *reinterpret_cast<SegSmem<ITEMS> *>(seg_smem_raw);
-    constexpr int kMaxN = kSegThreads * ITEMS, kMinN = kMaxN / 2;
     __shared__ uint32_t s_long[kSegThreads];
     __shared__ uint32_t s_n_long;
     const uint32_t tid = threadIdx.x;
@@ -549,107 +616,22 @@ segment_sort_long_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bit
     for (uint32_t s0 = slot_begin; s0 < slot_end; s0 += kSegThreads) {
         if (tid == 0) s_n_long = 0;
         __syncthreads();
-        if (s0 + tid < slot_end) {
-            const int32_t n = segment_of(s0 + tid, n_slots, n_tiles, tile_n_bits, offsets, n_total).n;
-            if (n > kMinN && n <= kMaxN) s_long[atomicAdd(&s_n_long, 1u)] = s0 + tid;
-        }
+        if (s0 + tid < slot_end && segment_of(s0 + tid, n_slots, n_tiles, tile_n_bits, offsets, n_total).n > kSegMax)
+            s_long[atomicAdd(&s_n_long, 1u)] = s0 + tid;
         __syncthreads();
         const uint32_t n_long = s_n_long;
         for (uint32_t li = 0; li < n_long; ++li) {
             const SegRange seg = segment_of(s_long[li], n_slots, n_tiles, tile_n_bits, offsets, n_total);
-            sort_segment_shared<ITEMS>(sm, seg, keyval, isect_ids, flatten_ids);
+            if (seg.n <= kSegThreads * kSegItemsMid)
+                sort_segment_shared<kSegItemsMid>(*reinterpret_cast<SegSmem<kSegItemsMid> *>(seg_smem_raw), seg, keyval,
+                                                  isect_ids, flatten_ids);
+            else if (seg.n <= kSegMaxShared)
+                sort_segment_shared<kSegItemsLong>(*reinterpret_cast<SegSmem<kSegItemsLong> *>(seg_smem_raw), seg,
+                                                   keyval, isect_ids, flatten_ids);
+            else
+                sort_segment_global(seg, keyval, alt, isect_ids, flatten_ids);
             __syncthreads();  // the next segment reuses the shared buffers
         }
-    }
-}
-
-// Long segments (n > kSegMaxShared = 8192): LSD radix sort of the full 64-bit words (depth_bits << 32 | id: unique, so no tie
-// pass) in global memory, ping-ponging between the segment's span of `keyval` and of `alt`.  One CTA per segment,
-// found by striding over the slots; correctness for any length matters here, speed does not.
-__global__ void __launch_bounds__(kSegThreads)
-segment_sort_big_kernel(uint32_t n_slots, uint32_t n_tiles, uint32_t tile_n_bits, const int32_t *__restrict__ offsets,
-                        const int64_t *__restrict__ n_isects_dev, int64_t capacity, uint64_t *keyval, uint64_t *alt,
-                        int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
-    __shared__ uint32_t s_cnt[kSegWarps * 256];
-    __shared__ uint32_t s_base[256];
-    __shared__ uint32_t s_tmp[kSegWarps];
-    __shared__ unsigned long long s_or[kSegWarps];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t n_total = min(*n_isects_dev, capacity);
-    // each CTA owns a contiguous range of slots and first finds the long ones with all threads in parallel
-    __shared__ uint32_t s_long[kSegThreads];
-    __shared__ uint32_t s_n_long;
-    const uint32_t per_cta = (n_slots + gridDim.x - 1) / gridDim.x;
-    const uint32_t slot_begin = blockIdx.x * per_cta, slot_end = min(n_slots, slot_begin + per_cta);
-    for (uint32_t s0 = slot_begin; s0 < slot_end; s0 += kSegThreads) {
-      if (tid == 0) s_n_long = 0;
-      __syncthreads();
-      if (s0 + tid < slot_end && segment_of(s0 + tid, n_slots, n_tiles, tile_n_bits, offsets, n_total).n > kSegMaxShared)
-          s_long[atomicAdd(&s_n_long, 1u)] = s0 + tid;
-      __syncthreads();
-      const uint32_t n_long = s_n_long;
-      for (uint32_t li = 0; li < n_long; ++li) {
-        const uint32_t slot = s_long[li];
-        const SegRange seg = segment_of(slot, n_slots, n_tiles, tile_n_bits, offsets, n_total);
-        const int32_t n = seg.n;
-        uint64_t *src = keyval + seg.start, *dst = alt + seg.start;
-        // bits that differ anywhere in the segment
-        const uint64_t first = src[0];
-        unsigned long long diff = 0ull;
-        for (int32_t i = (int32_t)tid; i < n; i += kSegThreads) diff |= src[i] ^ first;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, off);
-        __syncthreads();
-        if (lane == 0) s_or[warp] = diff;
-        __syncthreads();
-#pragma unroll
-        for (int w = 0; w < kSegWarps; ++w) diff |= s_or[w];
-
-        const int32_t chunk = (int32_t)(((int64_t)n + kSegThreads - 1) / kSegThreads) * 32;
-        const int32_t wbase = (int32_t)warp * chunk;
-        uint32_t *my_cnt = s_cnt + warp * 256;
-        for (int shift = 0; shift < 64; shift += 8) {
-            if (((diff >> shift) & 0xffull) == 0ull) continue;  // this digit is constant: the pass is the identity
-#pragma unroll
-            for (int k = 0; k < kSegWarps; ++k) s_cnt[k * 256 + tid] = 0;
-            __syncthreads();
-            for (int32_t e0 = wbase; e0 < wbase + chunk && e0 < n; e0 += 32) {
-                const int32_t e = e0 + (int32_t)lane;
-                const bool valid = e < n;
-                const uint32_t d = valid ? (uint32_t)((src[e] >> shift) & 0xffull) : 0u;
-                (void)warp_rank_digit(d, valid, my_cnt, lane);
-            }
-            __syncthreads();
-            uint32_t cnt_d = 0;
-#pragma unroll
-            for (int w = 0; w < kSegWarps; ++w) {
-                const uint32_t c = s_cnt[w * 256 + tid];
-                s_cnt[w * 256 + tid] = cnt_d;
-                cnt_d += c;
-            }
-            s_base[tid] = block_exclusive_scan_u32_256(cnt_d, s_tmp);
-            __syncthreads();
-            // second walk: the counters now run from each warp's exclusive offset
-            for (int32_t e0 = wbase; e0 < wbase + chunk && e0 < n; e0 += 32) {
-                const int32_t e = e0 + (int32_t)lane;
-                const bool valid = e < n;
-                const uint64_t kv = valid ? src[e] : 0ull;
-                const uint32_t d = valid ? (uint32_t)((kv >> shift) & 0xffull) : 0u;
-                const uint32_t r = warp_rank_digit(d, valid, my_cnt, lane);
-                if (valid) dst[s_base[d] + r] = kv;
-            }
-            __syncthreads();
-            uint64_t *t = src;
-            src = dst;
-            dst = t;
-        }
-        for (int32_t i = (int32_t)tid; i < n; i += kSegThreads) {
-            const uint64_t kv = src[i];
-            isect_ids[seg.start + i] = (int64_t)(seg.hi | (kv >> 32));
-            flatten_ids[seg.start + i] = (int32_t)(uint32_t)kv;
-        }
-        __syncthreads();
-      }
     }
 }
 
@@ -736,11 +718,7 @@ extern "C" int ubs_isect_bin_sort(int C, int64_t N, const float *means2d, const 
     if (!seg_attr_set) {
         UBS_CUDA_TRY(cudaFuncSetAttribute(segment_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(SegSmem<kSegItems>)));
-        UBS_CUDA_TRY(cudaFuncSetAttribute(segment_sort_long_kernel<kSegItemsMid>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(SegSmem<kSegItemsMid>)));
-        UBS_CUDA_TRY(cudaFuncSetAttribute(segment_sort_long_kernel<kSegItemsLong>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+        UBS_CUDA_TRY(cudaFuncSetAttribute(segment_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(SegSmem<kSegItemsLong>)));
         seg_attr_set = true;
     }
@@ -748,18 +726,11 @@ extern "C" int ubs_isect_bin_sort(int C, int64_t N, const float *means2d, const 
         n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects, capacity, w.keyval, isect_ids, flatten_ids);
     UBS_LAUNCH_CHECK("segment_sort_kernel");
     if (capacity > kSegMax) {  // a tile of more than 2048 pairs is possible at all
-        const unsigned g_mid = n_slots < (unsigned)(2 * sm) ? n_slots : (unsigned)(2 * sm);
-        segment_sort_long_kernel<kSegItemsMid><<<g_mid, kSegThreads, sizeof(SegSmem<kSegItemsMid>), s>>>(
-            n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects, capacity, w.keyval, isect_ids, flatten_ids);
-        UBS_LAUNCH_CHECK("segment_sort_long_kernel");
         const unsigned g_long = n_slots < (unsigned)sm ? n_slots : (unsigned)sm;
-        segment_sort_long_kernel<kSegItemsLong><<<g_long, kSegThreads, sizeof(SegSmem<kSegItemsLong>), s>>>(
-            n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects, capacity, w.keyval, isect_ids, flatten_ids);
+        segment_sort_long_kernel<<<g_long, kSegThreads, sizeof(SegSmem<kSegItemsLong>), s>>>(
+            n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects, capacity, w.keyval, w.alt, isect_ids,
+            flatten_ids);
         UBS_LAUNCH_CHECK("segment_sort_long_kernel");
     }
-    const unsigned big_grid = n_slots < (unsigned)(2 * sm) ? n_slots : (unsigned)(2 * sm);
-    segment_sort_big_kernel<<<big_grid, kSegThreads, 0, s>>>(n_slots, n_tiles, (uint32_t)tile_n_bits, offsets, n_isects,
-                                                             capacity, w.keyval, w.alt, isect_ids, flatten_ids);
-    UBS_LAUNCH_CHECK("segment_sort_big_kernel");
     return UBS_OK;
 }
