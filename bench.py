@@ -332,10 +332,19 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         # rows sharded over the ranks: gradient tiles go over NVLink into the owner's staging buffer from inside the
         # projection-backward kernel, the owner reduces + applies Adam and stores the new rows into every rank
-        sharded = parallel.ShardedState.create(D, N)
-        sharded.records.copy_(rec)
-        del rec_train
-        rec_train = sharded.records
+        try:
+            sharded = parallel.ShardedState.create(D, N)
+        except Exception as e:  # symmetric memory unavailable on this box: the NCCL path still measures the step
+            sys.stderr.write("bench.py: sharded step unavailable (%s); using the NCCL all-reduce path\n" % (e,))
+            sharded = None
+        ok = torch.tensor([1 if sharded is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok.item()):
+            sharded = None
+        if sharded is not None:
+            sharded.records.copy_(rec)
+            del rec_train
+            rec_train = sharded.records
     tstep = training.TrainStep(rz, training.PackedAdam(D, N, device=dev, allocate_moments=sharded is None), world=world,
                                sharded=sharded)
 
@@ -346,6 +355,7 @@ def run_ours(args, rank, local_rank, world):
 
     ms_full, launches_full, clocks_full, stages_full = timed(train_full, args.steps, args.warmup, True)
     its_full = world * args.steps / (ms_full / 1e3)
+    used_sharded = sharded is not None
     del rec_train, tstep, sharded
     nccl_full = None
     if world > 1:
@@ -500,6 +510,7 @@ def run_ours(args, rank, local_rank, world):
                        "gpu_launches": launches_full, "clocks": clocks_full,
                        "stages_ms": {k: v[1] for k, v in stages_full.items()},
                        "update": ("Adam inside the projection-backward kernel" if world == 1 else
+                                  "chunk-pipelined NCCL all-reduce + Adam on every rank" if not used_sharded else
                                   "rows sharded over the ranks: NVLink peer stores from the projection-backward "
                                   "kernel into the owner's staging buffer, owner-side reduce + Adam + parameter "
                                   "stores to every rank (symmetric memory)"),
