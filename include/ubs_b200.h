@@ -316,6 +316,12 @@ int ubs_reduce_adam_gather(int64_t N, int D, int world, int rank, int64_t shard_
 int ubs_mcmc_relocate(int64_t N, int D, float *records, float *exp_avg, float *exp_avg_sq, int64_t K,
                       const int64_t *dst_idx, const int64_t *src_idx, int32_t *counts, void *stream);
 
+/* SGLD position noise of the MCMC densification step (train.py:156-163): xyz += Sigma_xyz (noise (1 - sigmoid(raw
+ * opacity))^100 noise_lr xyz_lr), Sigma_xyz = BetaModel.get_xyz_covariance (scene/beta_model.py:143-152, the
+ * spatial_block of rot_scale_l_triangle_to_covar).  noise: [N,3] N(0,1) draws made by the caller (torch.randn_like
+ * defines them).  In place on the xyz columns of the records.                                                   */
+int ubs_sgld_noise(int64_t N, int D, float *records, const float *noise, double noise_lr, double xyz_lr, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,3 +110,19 @@ def add_new(params, moments, add_idx):
             v2[add_idx] = 0
             out_m.append((m2, v2))
     return out, out_m
+
+
+def sgld_noise(params, noise, noise_lr, xyz_lr):
+    """train.py:156-163 with the N(0,1) draw given: returns the new xyz.  get_xyz_covariance
+    (scene/beta_model.py:143-152) is the spatial block of rot_scale_l_triangle_to_covar on get_rotation / get_scale /
+    get_l_triangle -- the K1 / K2 restatements of oracle/ubs_oracle.py, which tests/test_oracle_golden.py pins against
+    the reference's _torch_impl fixtures (spatial_block included)."""
+    from oracle import ubs_oracle as O
+
+    xyz, mean, rgb, opacity, beta, scale, l_triangle = params
+    N = xyz.shape[0]
+    cov = O.rot_scale_l_triangle_to_covar(O.l_triangle_to_rotmat(l_triangle[:, :3]), F.softplus(scale), l_triangle,
+                                          spatial_block=True)
+    n = torch.randn_like(xyz) if noise is None else noise
+    n = n * torch.pow(1 - torch.sigmoid(opacity.reshape(N, 1)), 100) * noise_lr * xyz_lr
+    return xyz + torch.bmm(cov, n.unsqueeze(-1)).squeeze(-1)

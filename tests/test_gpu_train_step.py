@@ -159,6 +159,40 @@ def test_mcmc_relocate_and_add_match_oracle(D):
     compare(rec2, grown, gm)
 
 
+@pytest.mark.parametrize("D", [6, 7])
+def test_sgld_noise_matches_oracle(D):
+    """ubs_sgld_noise against the restated train.py:156-163 on the same N(0,1) draw (FP32 tolerance: 1e-5 relative to
+    the largest displacement of the row + 1e-7 absolute; every other record column untouched bit for bit)."""
+    from oracle import train_oracle as T
+    from ubs_b200 import fused, synth, training
+
+    N = 5000
+    scene = synth.make_scene(N, D, seed=17)
+    params = [t.clone() for t in scene.tensors()]
+    params[3] = params[3].reshape(N, 1)
+    g = torch.Generator().manual_seed(4)
+    params[3][torch.rand(N, generator=g) < 0.5] -= 6.0  # plenty of nearly transparent primitives: (1 - o)^100 ~ 1
+    noise = torch.randn(N, 3, generator=g)
+    noise_lr, xyz_lr = 5e5, 1.6e-4 * 0.37
+    want = T.sgld_noise(params, noise, noise_lr, xyz_lr)
+    rec = fused.pack_records(D, *[p.cuda() for p in params])
+    before = rec.clone()
+    out = training.sgld_noise(rec, D, noise_lr, xyz_lr, noise=noise.cuda())
+    assert torch.equal(out.cpu(), noise)
+    got = rec[:, :3].cpu()
+    moved = (want - params[0]).abs()
+    assert moved.max().item() > 1e-3  # the test exercises a visible displacement
+    tol = 1e-5 * moved.max(dim=1, keepdim=True).values + 1e-7 + 2e-7 * params[0].abs()
+    assert bool(((got - want).abs() <= tol).all()), (got - want).abs().max().item()
+    assert torch.equal(rec[:, 3:], before[:, 3:])
+    # default draw: torch's generator on the device defines the noise
+    gd = torch.Generator(device="cuda").manual_seed(11)
+    rec2 = before.clone()
+    n2 = training.sgld_noise(rec2, D, noise_lr, xyz_lr, generator=gd)
+    gd.manual_seed(11)
+    assert torch.equal(n2, torch.randn((N, 3), device="cuda", generator=gd))
+
+
 def test_train_step_reduces_loss_and_matches_manual_composition():
     """TrainStep.step == forward, loss kernel, backward, Adam composed by hand; and it learns."""
     from ubs_b200 import fused, synth, training

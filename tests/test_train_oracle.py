@@ -71,3 +71,25 @@ def test_packed_adam_lr_columns_follow_record_layout():
         assert sl["opacity"].start == D + 3 and sl["scale"].start == 2 * D + 2  # the columns csrc/optim.cu assumes
         assert sl["l_triangle"].stop <= fused.record_stride(D)
     assert set(DEFAULT_LR) == set(sl)
+
+
+def test_sgld_noise_oracle_properties():
+    """train.py:156-163: dead primitives (opacity -> 0) take the full covariance-shaped noise, opaque ones none; the
+    displacement is Sigma_xyz @ (noise * w) with the K1/K2 oracle that the _torch_impl fixtures pin."""
+    from oracle import train_oracle as T
+    from oracle import ubs_oracle as O
+
+    torch.manual_seed(3)
+    N, D = 64, 6
+    params = [torch.randn(N, w) * 0.3 for w in (3, 3, 3, 1, 4, 6, 15)]
+    params[3][:32] = -12.0   # (1 - sigmoid)^100 ~ 1
+    params[3][32:] = 3.0     # (1 - 0.95)^100 underflows to 0 in FP32
+    noise = torch.randn(N, 3)
+    new = T.sgld_noise(params, noise, 5e5, 1.6e-4)
+    assert torch.equal(new[32:], params[0][32:])
+    cov = O.rot_scale_l_triangle_to_covar(O.l_triangle_to_rotmat(params[6][:, :3]), torch.nn.functional.softplus(params[5]),
+                                          params[6], spatial_block=True)
+    w = (1 - torch.sigmoid(params[3][:32])) ** 100
+    want = torch.einsum("nij,nj->ni", cov[:32], noise[:32] * w * 5e5 * 1.6e-4)
+    assert torch.allclose(new[:32] - params[0][:32], want, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(cov, cov.transpose(1, 2))

@@ -136,6 +136,46 @@ relocate_fixup_kernel(int64_t K, int stride, int col_opacity, float *__restrict_
         }
 }
 
+// train.py:156-163 (every densification interval): xyz += Sigma_xyz (noise (1 - opacity)^100 noise_lr xyz_lr) with
+// Sigma_xyz = get_xyz_covariance = (R diag(s)) (R diag(s))^T, R = I + skew(l_triangle[:3]), s = softplus(scale[:3])
+// (rot_scale_l_triangle_to_covar_fwd.cu:28-49, spatial_block = true).  The N(0,1) draw (torch.randn_like) stays with
+// the caller: its values are defined by torch's RNG stream.  One thread per primitive; runs once per 100 iterations.
+__global__ void __launch_bounds__(256)
+sgld_noise_kernel(int64_t N, int stride, int D, float *__restrict__ records, const float *__restrict__ noise,
+                  float noise_lr, float xyz_lr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float *rec = records + i * stride;
+    // the library is built with --use_fast_math: sigmoid, softplus and the 100th power are evaluated in FP64 and
+    // rounded once (torch's CUDA kernels are precise-math FP32)
+    const float op = (float)(1.0 / (1.0 + exp(-(double)rec[D + 3])));
+    const float w = (float)pow((double)(1.f - op), 100.0);
+    float s[3], n[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float raw = rec[2 * D + 2 + k];
+        s[k] = raw > 20.f ? raw : (float)log1p(exp((double)raw));
+        n[k] = __fmul_rn(__fmul_rn(__fmul_rn(noise[i * 3 + k], w), noise_lr), xyz_lr);
+    }
+    const float a01 = rec[3 * D + 2], a02 = rec[3 * D + 3], a12 = rec[3 * D + 4];
+    const float R[9] = {1.f, a01, a02, -a01, 1.f, a12, -a02, -a12, 1.f};
+    float L[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) L[r * 3 + c] = __fmul_rn(R[r * 3 + c], s[c]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float cov = __fmaf_rn(L[r * 3 + 2], L[c * 3 + 2], __fmaf_rn(L[r * 3 + 1], L[c * 3 + 1], __fmul_rn(L[r * 3], L[c * 3])));
+            acc = __fmaf_rn(cov, n[c], acc);
+        }
+        rec[r] += acc;
+    }
+}
+
 }  // namespace
 }  // namespace ubs
 
@@ -224,5 +264,17 @@ extern "C" int ubs_reduce_adam_gather(int64_t N, int D, int world, int rank, int
         n_vec, stride / 4, row_begin, world, shard_rows * (stride / 4), (const float4 *)staging, (float4 *)exp_avg_shard,
         (float4 *)exp_avg_sq_shard, peers, (float4 *)mc_records, rank, a);
     UBS_LAUNCH_CHECK("reduce_adam_gather_kernel");
+    return UBS_OK;
+}
+
+extern "C" int ubs_sgld_noise(int64_t N, int D, float *records, const float *noise, double noise_lr, double xyz_lr,
+                              void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(N >= 0 && D >= 4 && D <= 8, "sgld_noise: bad sizes (N=%lld, D=%d)", (long long)N, D);
+    if (N == 0) return UBS_OK;
+    UBS_CHECK_ARG(records && noise, "sgld_noise: null pointer");
+    sgld_noise_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(N, UBS_RECORD_STRIDE(D), D, records, noise,
+                                                                            (float)noise_lr, (float)xyz_lr);
+    UBS_LAUNCH_CHECK("sgld_noise_kernel");
     return UBS_OK;
 }

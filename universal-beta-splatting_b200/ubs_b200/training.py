@@ -213,6 +213,23 @@ def mcmc_add(records: Tensor, D: int, src_idx: Tensor, adam: Optional[PackedAdam
     return grown
 
 
+@torch.no_grad()
+def sgld_noise(records: Tensor, D: int, noise_lr: float, xyz_lr: float, noise: Optional[Tensor] = None,
+               generator=None) -> Tensor:
+    """The position noise of the MCMC step (train.py:156-163), in place on the xyz columns:
+    xyz += get_xyz_covariance @ (randn * (1 - opacity)^100 * noise_lr * xyz_lr).  `noise` ([N,3], N(0,1)) defaults to a
+    torch.randn draw on the records' device (torch's RNG stream defines it, as in the reference).  Returns the noise."""
+    lib = _lib.load()
+    N = records.shape[0]
+    if noise is None:
+        noise = torch.randn((N, 3), dtype=torch.float32, device=records.device, generator=generator)
+    assert noise.shape == (N, 3) and noise.dtype == torch.float32 and noise.device == records.device
+    noise = noise.contiguous()
+    check(lib.ubs_sgld_noise(N, D, ptr(records), ptr(noise), float(noise_lr), float(xyz_lr),
+                             torch.cuda.current_stream().cuda_stream), "ubs_sgld_noise")
+    return noise
+
+
 def sample_alive(probs: Tensor, num: int, alive_indices: Optional[Tensor] = None, generator=None) -> Tensor:
     """_sample_alives (scene/beta_model.py:567-573) without the bincount: the multinomial draw itself is torch's
     (its result is defined by torch's RNG stream)."""
