@@ -119,3 +119,61 @@ def test_fused_backward_matches_reference_chain(D, N, W, H):
     assert (rec.grad[:, fused.record_slices(D)["l_triangle"].stop:] == 0).all()  # padding columns
     v_bg_ref = (v_rc * (1.0 - R["render_alphas"])).sum(dim=(1, 2))
     torch.testing.assert_close(bgl.grad, v_bg_ref, rtol=1e-3, atol=1e-6)
+
+
+def test_two_threads_two_streams_render_concurrently():
+    """SURVEY 8(b) threading row: the training thread renders while a viewer thread calls view() (train.py:95-98,177).
+    Two host threads, each on its own CUDA stream with its own FusedRasterizer, render different cameras of one shared
+    record buffer at the same time; every frame must be bit-identical to the same camera rendered alone, and a bad call
+    in one thread must not leak its error message into the other (thread-local error channel)."""
+    import threading
+
+    from ubs_b200 import _lib, fused, synth
+
+    D, N, W, H = 6, 80000, 480, 360
+    scene = synth.make_scene(N, D, seed=77).to("cuda")
+    cams = synth.make_cameras(6, W, H, seed=5, device="cuda")
+    bg = torch.tensor([[0.2, 0.2, 0.2]], device="cuda")
+    rec = fused.pack_records(D, *scene.tensors())
+    rz0 = fused.FusedRasterizer(D, N, W, H, n_cams=1)
+    want = []
+    for cam in cams:
+        rc, ra = rz0.forward(rec, cam.viewmat[None], cam.K[None], cam.cam_pos[None], None, bg)
+        want.append((rc.clone(), ra.clone()))
+    torch.cuda.synchronize()
+
+    lib = _lib.load()
+    errors, got = [], {}
+
+    def worker(tid):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                rz = fused.FusedRasterizer(D, N, W, H, n_cams=1)
+                for rep in range(4):
+                    for k in range(tid, len(cams), 2):
+                        cam = cams[k]
+                        rc, ra = rz.forward(rec, cam.viewmat[None], cam.K[None], cam.cam_pos[None], None, bg)
+                        got[(tid, rep, k)] = (rc.clone(), ra.clone())
+                    if tid == 1 and rep == 1:
+                        # an invalid call on this thread only: stride query with an unsupported dimension
+                        assert lib.ubs_record_stride(99) < 0
+                        assert lib.ubs_rasterize_fwd(1, 1, None, 0, None, None, None, None, None, None, None, 3, W, H, 7,
+                                                     None, None, None, None, None, None) < 0
+                        assert b"tile_size" in lib.ubs_last_error()
+                stream.synchronize()
+            if tid == 0:
+                assert b"tile_size" not in lib.ubs_last_error()
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+    assert len(got) == 4 * len(cams)
+    for (tid, rep, k), (rc, ra) in got.items():
+        assert torch.equal(rc, want[k][0]) and torch.equal(ra, want[k][1]), (tid, rep, k)
