@@ -34,6 +34,7 @@ constexpr int kSegItems = 8;                       // elements per thread in the
 constexpr int kSegMax = kSegThreads * kSegItems;   // longest segment of the first shared-memory instantiation
 constexpr int kSegItemsMid = 16, kSegItemsLong = 32;                 // 2049..4096 and 4097..8192 pairs per tile
 constexpr int kSegMaxShared = kSegThreads * kSegItemsLong;          // beyond this: sort_segment_global
+constexpr int kBucketMax = 64;  // MSD shortcut of the segment sort: largest bucket ranked by comparisons
 constexpr int kScanThreads = 1024;
 // Atomic targets are spread to one per 32-byte sector: with 4-byte spacing the whole cursor array sits in a few
 // L2 slices and one slice's atomic unit saturates (lts__d_atomic_input_cycles_active: max 65 %, mean 8.5 %).
@@ -480,6 +481,52 @@ __device__ __forceinline__ void sort_segment_shared(SegSmem<ITEMS> &sm, const Se
 
     // each warp owns a contiguous chunk (a multiple of 32 elements); order inside = (item, lane)
     const int32_t chunk = ((n + kSegThreads - 1) / kSegThreads) * 32;
+
+    // ---- MSD shortcut: ONE counting pass over the top (at most 9) varying depth bits, then every element ranks itself
+    // inside its bucket by comparing the full 64-bit words depth << 32 | id (unique, so this is the final order and
+    // the tie rule at once).  A tile holds a few hundred pairs spread over up to 512 buckets, so a bucket has a
+    // handful of members and the ranking costs less than the two LSD passes it replaces.  Segments whose depths
+    // cluster (a bucket above kBucketMax members) take the LSD passes below instead.
+    if (nbits > 0) {
+        const int top_w = nbits < 9 ? nbits : 9, top_shift = nbits - top_w;
+        const int ndig = 1 << top_w;
+        // The bucket pass need not be stable (the comparisons below define the order), so it is a plain counting
+        // sort with shared-memory atomics: histogram, exclusive scan (two digits per thread), cursor scatter.
+        uint32_t *start = sm.cnt, *cursor = sm.cnt + 512;  // first position / next free position of every bucket
+        for (int d = (int)tid; d < 512; d += kSegThreads) cursor[d] = 0u;
+        __syncthreads();
+        const unsigned long long *A = sm.kv[0];
+        for (int32_t i = (int32_t)tid; i < n; i += kSegThreads)
+            atomicAdd(&cursor[(uint32_t)(A[i] >> 32) >> top_shift], 1u);
+        __syncthreads();
+        const uint32_t c0 = cursor[2 * tid], c1 = cursor[2 * tid + 1];
+        const uint32_t ex = block_exclusive_scan_u32_256(c0 + c1, sm.tmp);  // contains two barriers
+        start[2 * tid] = ex, start[2 * tid + 1] = ex + c0;
+        cursor[2 * tid] = ex, cursor[2 * tid + 1] = ex + c0;
+        const bool big = c0 > (uint32_t)kBucketMax || c1 > (uint32_t)kBucketMax;
+        if (!__syncthreads_or(big)) {
+            for (int32_t i = (int32_t)tid; i < n; i += kSegThreads) {
+                const unsigned long long e = A[i];
+                sm.kv[1][atomicAdd(&cursor[(uint32_t)(e >> 32) >> top_shift], 1u)] = e;
+            }
+            __syncthreads();
+            const unsigned long long *B = sm.kv[1];
+            int64_t *keys_out = isect_ids + seg.start;
+            int32_t *vals_out = flatten_ids + seg.start;
+            for (int32_t i = (int32_t)tid; i < n; i += kSegThreads) {
+                const unsigned long long e = B[i];
+                const uint32_t k = (uint32_t)(e >> 32);
+                const int d = (int)(k >> top_shift);
+                const uint32_t b0 = start[d], b1 = d + 1 < ndig ? start[d + 1] : (uint32_t)n;
+                uint32_t pos = b0;
+#pragma unroll 4
+                for (uint32_t j = b0; j < b1; ++j) pos += B[j] < e;
+                keys_out[pos] = (int64_t)(seg.hi | (uint64_t)(k + lo));
+                vals_out[pos] = (int32_t)(uint32_t)e;
+            }
+            return;
+        }
+    }
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
         const int shift = p * width;
