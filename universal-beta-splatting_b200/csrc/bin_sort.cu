@@ -34,6 +34,7 @@ constexpr int kSegItems = 8;                       // elements per thread in the
 constexpr int kSegMax = kSegThreads * kSegItems;   // longest segment of the first shared-memory instantiation
 constexpr int kSegItemsMid = 16, kSegItemsLong = 32;                 // 2049..4096 and 4097..8192 pairs per tile
 constexpr int kSegMaxShared = kSegThreads * kSegItemsLong;          // beyond this: sort_segment_global
+constexpr int kTopBits = 11;    // MSD shortcut of the segment sort: bucket = top 11 varying depth bits
 constexpr int kBucketMax = 64;  // MSD shortcut of the segment sort: largest bucket ranked by comparisons
 constexpr int kScanThreads = 1024;
 // Atomic targets are spread to one per 32-byte sector: with 4-byte spacing the whole cursor array sits in a few
@@ -482,28 +483,53 @@ __device__ __forceinline__ void sort_segment_shared(SegSmem<ITEMS> &sm, const Se
     // each warp owns a contiguous chunk (a multiple of 32 elements); order inside = (item, lane)
     const int32_t chunk = ((n + kSegThreads - 1) / kSegThreads) * 32;
 
-    // ---- MSD shortcut: ONE counting pass over the top (at most 9) varying depth bits, then every element ranks itself
+    // ---- MSD shortcut: ONE counting pass over the top (at most kTopBits) varying depth bits, then every element ranks itself
     // inside its bucket by comparing the full 64-bit words depth << 32 | id (unique, so this is the final order and
-    // the tie rule at once).  A tile holds a few hundred pairs spread over up to 512 buckets, so a bucket has a
+    // the tie rule at once).  A tile holds a few hundred pairs spread over up to 2048 buckets, so a bucket has a
     // handful of members and the ranking costs less than the two LSD passes it replaces.  Segments whose depths
     // cluster (a bucket above kBucketMax members) take the LSD passes below instead.
     if (nbits > 0) {
-        const int top_w = nbits < 9 ? nbits : 9, top_shift = nbits - top_w;
+        const int cap_w = n >= 768 ? kTopBits : kTopBits - 2;  // short segments: fewer, fuller buckets measure faster
+        const int top_w = nbits < cap_w ? nbits : cap_w, top_shift = nbits - top_w;
         const int ndig = 1 << top_w;
         // The bucket pass need not be stable (the comparisons below define the order), so it is a plain counting
         // sort with shared-memory atomics: histogram, exclusive scan (two digits per thread), cursor scatter.
-        uint32_t *start = sm.cnt, *cursor = sm.cnt + 512;  // first position / next free position of every bucket
-        for (int d = (int)tid; d < 512; d += kSegThreads) cursor[d] = 0u;
+        constexpr int kDig = 1 << kTopBits, kPer = kDig / kSegThreads;  // digits, digits per thread in the scan
+        static_assert(2 * kDig <= kSegWarps * 512 && kPer % 4 == 0, "bucket tables live in the counter array");
+        uint32_t *start = sm.cnt, *cursor = sm.cnt + kDig;  // first position / next free position of every bucket
+#pragma unroll
+        for (int q = 0; q < kPer / 4; ++q)
+            reinterpret_cast<uint4 *>(cursor)[tid * (kPer / 4) + q] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
         const unsigned long long *A = sm.kv[0];
         for (int32_t i = (int32_t)tid; i < n; i += kSegThreads)
             atomicAdd(&cursor[(uint32_t)(A[i] >> 32) >> top_shift], 1u);
         __syncthreads();
-        const uint32_t c0 = cursor[2 * tid], c1 = cursor[2 * tid + 1];
-        const uint32_t ex = block_exclusive_scan_u32_256(c0 + c1, sm.tmp);  // contains two barriers
-        start[2 * tid] = ex, start[2 * tid + 1] = ex + c0;
-        cursor[2 * tid] = ex, cursor[2 * tid + 1] = ex + c0;
-        const bool big = c0 > (uint32_t)kBucketMax || c1 > (uint32_t)kBucketMax;
+        uint32_t c[kPer], sum = 0;
+        bool big = false;
+#pragma unroll
+        for (int q = 0; q < kPer / 4; ++q) {
+            const uint4 v = reinterpret_cast<const uint4 *>(cursor)[tid * (kPer / 4) + q];
+            c[4 * q] = v.x, c[4 * q + 1] = v.y, c[4 * q + 2] = v.z, c[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            sum += c[q];
+            big |= c[q] > (uint32_t)kBucketMax;
+        }
+        uint32_t run = block_exclusive_scan_u32_256(sum, sm.tmp);  // contains two barriers
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const uint32_t t = c[q];
+            c[q] = run;
+            run += t;
+        }
+#pragma unroll
+        for (int q = 0; q < kPer / 4; ++q) {
+            const uint4 v = make_uint4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+            reinterpret_cast<uint4 *>(start)[tid * (kPer / 4) + q] = v;
+            reinterpret_cast<uint4 *>(cursor)[tid * (kPer / 4) + q] = v;
+        }
         if (!__syncthreads_or(big)) {
             for (int32_t i = (int32_t)tid; i < n; i += kSegThreads) {
                 const unsigned long long e = A[i];
