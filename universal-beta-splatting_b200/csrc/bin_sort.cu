@@ -444,12 +444,20 @@ __device__ __forceinline__ void sort_segment_shared(SegSmem<ITEMS> &sm, const Se
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t *src = keyval + seg.start;
 
-    // ---- depth range of the segment; keys are stored relative to the smallest one ------------------------------
+    // bucket tables of the MSD shortcut below (they live in the counter array of the LSD passes)
+    constexpr int kDig = 1 << kTopBits, kPer = kDig / kSegThreads;  // digits, digits per thread in the scan
+    static_assert(2 * kDig <= kSegWarps * 512 && kPer % 4 == 0, "bucket tables live in the counter array");
+    uint32_t *start = sm.cnt, *hist = sm.cnt + kDig;  // first position / number of members of every bucket
+#pragma unroll
+    for (int q = 0; q < kPer / 4; ++q) reinterpret_cast<uint4 *>(hist)[tid * (kPer / 4) + q] = make_uint4(0u, 0u, 0u, 0u);
+
+    // ---- depth range of the segment; keys are taken relative to the smallest one -------------------------------
     unsigned long long mine[ITEMS];
     uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
         const int32_t i = it * kSegThreads + (int32_t)tid;
+        mine[it] = 0ull;
         if (i < n) {
             mine[it] = src[i];
             const uint32_t k = (uint32_t)(mine[it] >> 32);
@@ -471,45 +479,35 @@ __device__ __forceinline__ void sort_segment_shared(SegSmem<ITEMS> &sm, const Se
     }
     const uint32_t lo = kmin;
 #pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-        const int32_t i = it * kSegThreads + (int32_t)tid;
-        if (i < n) sm.kv[0][i] = mine[it] - ((unsigned long long)lo << 32);
-    }
+    for (int it = 0; it < ITEMS; ++it) mine[it] -= (unsigned long long)lo << 32;  // (slots past n are never used)
     const int nbits = 32 - __clz(kmax - kmin);  // 0 when every depth is identical
     const int passes = (nbits + 8) / 9;         // digits of at most 9 bits
     const int width = passes > 0 ? (nbits + passes - 1) / passes : 0;
-    __syncthreads();
 
-    // each warp owns a contiguous chunk (a multiple of 32 elements); order inside = (item, lane)
-    const int32_t chunk = ((n + kSegThreads - 1) / kSegThreads) * 32;
-
-    // ---- MSD shortcut: ONE counting pass over the top (at most kTopBits) varying depth bits, then every element ranks itself
-    // inside its bucket by comparing the full 64-bit words depth << 32 | id (unique, so this is the final order and
-    // the tie rule at once).  A tile holds a few hundred pairs spread over up to 2048 buckets, so a bucket has a
-    // handful of members and the ranking costs less than the two LSD passes it replaces.  Segments whose depths
-    // cluster (a bucket above kBucketMax members) take the LSD passes below instead.
+    // ---- MSD shortcut: ONE counting pass over the top (at most kTopBits) varying depth bits, then every element
+    // ranks itself inside its bucket by comparing the full 64-bit words depth << 32 | id (unique, so this is the final
+    // order and the tie rule at once).  A tile holds a few hundred pairs spread over up to 2048 buckets, so a bucket
+    // has a handful of members and the ranking costs less than the LSD passes it replaces.  The bucket pass need not
+    // be stable, so it is a counting sort with ONE shared-memory atomic per element, issued from the registers the
+    // element was loaded into: the returned count is the element's slot inside its bucket (spread-address ATOMS cost
+    // 2 cycles per lane -- the pass is bound by them).  Segments whose depths cluster (a bucket above kBucketMax
+    // members) take the LSD passes below instead.
     if (nbits > 0) {
         const int cap_w = n >= 768 ? kTopBits : kTopBits - 2;  // short segments: fewer, fuller buckets measure faster
         const int top_w = nbits < cap_w ? nbits : cap_w, top_shift = nbits - top_w;
         const int ndig = 1 << top_w;
-        // The bucket pass need not be stable (the comparisons below define the order), so it is a plain counting
-        // sort with shared-memory atomics: histogram, exclusive scan (two digits per thread), cursor scatter.
-        constexpr int kDig = 1 << kTopBits, kPer = kDig / kSegThreads;  // digits, digits per thread in the scan
-        static_assert(2 * kDig <= kSegWarps * 512 && kPer % 4 == 0, "bucket tables live in the counter array");
-        uint32_t *start = sm.cnt, *cursor = sm.cnt + kDig;  // first position / next free position of every bucket
+        uint32_t slot[ITEMS];
 #pragma unroll
-        for (int q = 0; q < kPer / 4; ++q)
-            reinterpret_cast<uint4 *>(cursor)[tid * (kPer / 4) + q] = make_uint4(0u, 0u, 0u, 0u);
-        __syncthreads();
-        const unsigned long long *A = sm.kv[0];
-        for (int32_t i = (int32_t)tid; i < n; i += kSegThreads)
-            atomicAdd(&cursor[(uint32_t)(A[i] >> 32) >> top_shift], 1u);
+        for (int it = 0; it < ITEMS; ++it) {
+            slot[it] = 0u;
+            if (it * kSegThreads + (int32_t)tid < n) slot[it] = atomicAdd(&hist[(uint32_t)(mine[it] >> 32) >> top_shift], 1u);
+        }
         __syncthreads();
         uint32_t c[kPer], sum = 0;
         bool big = false;
 #pragma unroll
         for (int q = 0; q < kPer / 4; ++q) {
-            const uint4 v = reinterpret_cast<const uint4 *>(cursor)[tid * (kPer / 4) + q];
+            const uint4 v = reinterpret_cast<const uint4 *>(hist)[tid * (kPer / 4) + q];
             c[4 * q] = v.x, c[4 * q + 1] = v.y, c[4 * q + 2] = v.z, c[4 * q + 3] = v.w;
         }
 #pragma unroll
@@ -525,16 +523,13 @@ __device__ __forceinline__ void sort_segment_shared(SegSmem<ITEMS> &sm, const Se
             run += t;
         }
 #pragma unroll
-        for (int q = 0; q < kPer / 4; ++q) {
-            const uint4 v = make_uint4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
-            reinterpret_cast<uint4 *>(start)[tid * (kPer / 4) + q] = v;
-            reinterpret_cast<uint4 *>(cursor)[tid * (kPer / 4) + q] = v;
-        }
+        for (int q = 0; q < kPer / 4; ++q)
+            reinterpret_cast<uint4 *>(start)[tid * (kPer / 4) + q] = make_uint4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
         if (!__syncthreads_or(big)) {
-            for (int32_t i = (int32_t)tid; i < n; i += kSegThreads) {
-                const unsigned long long e = A[i];
-                sm.kv[1][atomicAdd(&cursor[(uint32_t)(e >> 32) >> top_shift], 1u)] = e;
-            }
+#pragma unroll
+            for (int it = 0; it < ITEMS; ++it)
+                if (it * kSegThreads + (int32_t)tid < n)
+                    sm.kv[1][start[(uint32_t)(mine[it] >> 32) >> top_shift] + slot[it]] = mine[it];
             __syncthreads();
             const unsigned long long *B = sm.kv[1];
             int64_t *keys_out = isect_ids + seg.start;
@@ -553,6 +548,16 @@ __device__ __forceinline__ void sort_segment_shared(SegSmem<ITEMS> &sm, const Se
             return;
         }
     }
+
+    // ---- LSD passes (clustered depths, or all depths identical) ------------------------------------------------
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int32_t i = it * kSegThreads + (int32_t)tid;
+        if (i < n) sm.kv[0][i] = mine[it];
+    }
+    __syncthreads();
+    // each warp owns a contiguous chunk (a multiple of 32 elements); order inside = (item, lane)
+    const int32_t chunk = ((n + kSegThreads - 1) / kSegThreads) * 32;
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
         const int shift = p * width;
