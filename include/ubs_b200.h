@@ -197,6 +197,23 @@ int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_c
 /* Diagnostic work counters for the compositing roofline (no reference counterpart):
  * counts[8] (device u64) = { E_test, E_acc, E_cull, pairs staged, E_any, E_cull4, E_any4, E_any8x2 } -- see
  * csrc/rasterize_fwd.cu.                                                                                    */
+/* The same two kernels gathering from the 48-byte splat rows ubs_fused_project_fwd writes (two sectors per pair
+ * instead of five: the compositing kernels are sensitive to what stays in L1).  colors: NULL = the RGB stored in the
+ * rows (channels must be 3), else a [C,N,channels] array as above (depth / feature channels of the viewer modes).
+ * The gradient outputs of the backward stay separate arrays (they feed ubs_fused_project_bwd).                 */
+int ubs_rasterize_fwd_splats(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
+                             const float *splats, /* [C,N,12] */
+                             const float *colors, const float *backgrounds, const uint8_t *masks, int channels,
+                             int width, int height, int tile_size, const int32_t *offsets,
+                             const int32_t *flatten_ids, float *render_colors, float *render_alphas,
+                             int32_t *last_ids, void *stream);
+int ubs_rasterize_bwd_splats(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
+                             const float *splats, const float *colors, const float *backgrounds,
+                             const uint8_t *masks, int channels, int width, int height, int tile_size,
+                             const int32_t *offsets, const int32_t *flatten_ids, const float *render_alphas,
+                             const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
+                             float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, float *v_betas,
+                             void *stream);
 int ubs_rasterize_count(int C, const int64_t *n_isects, int64_t isect_capacity, const float *means2d,
                         const float *conics, const float *opacities, const float *betas, int width, int height,
                         int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
@@ -235,6 +252,10 @@ int ubs_fused_project_fwd(int C, int64_t N, int D, const float *records, /* [N, 
                           float *betas,             /* [C,N] spatial beta = 4 exp(raw beta_0) */
                           float *colors,            /* [C,N,3] or NULL (rgb copied out of the record) */
                           int32_t *tiles_per_gauss, /* [C,N] */
+                          float *splats,            /* NULL, or [C,N,12]: the visible primitives' screen-space records
+                                                       once more as 48-byte rows (mean2d.xy, opacity, beta | conic abc,
+                                                       depth | rgb, 0) for ubs_rasterize_{fwd,bwd}_splats; rows of
+                                                       culled primitives are left untouched */
                           int32_t *tile_delta,      /* NULL or start of the bin-sort workspace (see above) */
                           int64_t *n_isects,        /* [1] device (may be NULL when tile_delta is given) */
                           void *workspace, size_t workspace_bytes, /* ubs_isect_workspace_bytes(C*N, cap); unused

@@ -177,3 +177,62 @@ def test_two_threads_two_streams_render_concurrently():
     assert len(got) == 4 * len(cams)
     for (tid, rep, k), (rc, ra) in got.items():
         assert torch.equal(rc, want[k][0]) and torch.equal(ra, want[k][1]), (tid, rep, k)
+
+
+def test_splat_rows_equal_the_separate_arrays_and_both_compositing_entries_agree():
+    """The fused projection writes every visible primitive's screen-space record twice: as the separate arrays of the
+    reference (radii, means2d, conics, ...) and as one 48-byte row (`splats`) that the compositing kernels gather from.
+    The rows must equal the arrays bit for bit, and ubs_rasterize_{fwd,bwd}_splats must give bit-identical images and
+    gradients to ubs_rasterize_{fwd,bwd} on the arrays (also with an explicit colour array, the viewer's path)."""
+    from ubs_b200 import _lib, fused, ops, synth
+    from ubs_b200._lib import check, ptr
+
+    D, N, W, H = 6, 70000, 400, 304
+    scene = synth.make_scene(N, D, seed=91).to("cuda")
+    cam = synth.make_cameras(1, W, H, seed=8, device="cuda")[0]
+    bg = torch.tensor([[0.3, 0.1, 0.6]], device="cuda")
+    rec = fused.pack_records(D, *scene.tensors())
+    rz = fused.FusedRasterizer(D, N, W, H, n_cams=1)
+    rc, ra = rz.forward(rec, cam.viewmat[None], cam.K[None], cam.cam_pos[None], None, bg)
+    vis = (rz.radii > 0)[0]
+    assert int(vis.sum()) > 1000
+    sp = rz.splats[0][vis]
+    assert torch.equal(sp[:, 0:2], rz.means2d[0][vis]) and torch.equal(sp[:, 2], rz.opacities[0][vis])
+    assert torch.equal(sp[:, 3], rz.betas[0][vis]) and torch.equal(sp[:, 4:7], rz.conics[0][vis])
+    assert torch.equal(sp[:, 7], rz.depths[0][vis]) and torch.equal(sp[:, 8:11], rz.colors[0][vis])
+
+    # the reference-shaped operator on the separate arrays
+    n = rz.last_pair_count()
+    rc2, ra2, last2 = ops.rasterize_fwd(rz.means2d, rz.conics, rz.colors, rz.opacities, rz.betas, bg, None, W, H, 16,
+                                        rz.offsets, rz.flatten_ids[:n])
+    assert torch.equal(rc2, rc) and torch.equal(ra2, ra) and torch.equal(last2, rz.last_ids)
+
+    lib, s = _lib.load(), torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(3)
+    v_rc = torch.randn(1, H, W, 3, device="cuda", generator=g) / (H * W)
+    v_ra = torch.randn(1, H, W, 1, device="cuda", generator=g) / (H * W)
+
+    def grads(use_splats, colors):
+        out = [torch.zeros_like(t) for t in (rz.means2d, rz.conics, rz.colors, rz.opacities, rz.betas)]
+        if use_splats:
+            check(lib.ubs_rasterize_bwd_splats(1, N, ptr(rz.n_isects), rz.capacity, ptr(rz.splats), ptr(colors), ptr(bg), None,
+                                               3, W, H, 16, ptr(rz.offsets), ptr(rz.flatten_ids), ptr(rz.render_alphas),
+                                               ptr(rz.last_ids), ptr(v_rc), ptr(v_ra), *[ptr(t) for t in out], s), "bwd_splats")
+        else:
+            check(lib.ubs_rasterize_bwd(1, N, ptr(rz.n_isects), rz.capacity, ptr(rz.means2d), ptr(rz.conics), ptr(rz.colors),
+                                        ptr(rz.opacities), ptr(rz.betas), ptr(bg), None, 3, W, H, 16, ptr(rz.offsets),
+                                        ptr(rz.flatten_ids), ptr(rz.render_alphas), ptr(rz.last_ids), ptr(v_rc), ptr(v_ra),
+                                        *[ptr(t) for t in out], s), "bwd")
+        return out
+
+    # gradients are sums of float atomics: equal up to the order of the additions
+    ref = grads(False, None)
+    for variant in (grads(True, None), grads(True, rz.colors)):
+        for a, b in zip(variant, ref):
+            assert (a - b).abs().max().item() <= 1e-6 * b.abs().max().item() + 1e-12
+    # forward with an explicit colour array next to the splat rows
+    rc3, ra3, last3 = torch.empty_like(rc), torch.empty_like(ra), torch.empty_like(rz.last_ids)
+    check(lib.ubs_rasterize_fwd_splats(1, N, ptr(rz.n_isects), rz.capacity, ptr(rz.splats), ptr(rz.colors), ptr(bg), None, 3,
+                                       W, H, 16, ptr(rz.offsets), ptr(rz.flatten_ids), ptr(rc3), ptr(ra3), ptr(last3), s),
+          "fwd_splats")
+    assert torch.equal(rc3, rc) and torch.equal(ra3, ra) and torch.equal(last3, rz.last_ids)

@@ -29,7 +29,7 @@ rasterize_bwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
                      const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
                      const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
                      float *__restrict__ v_conics, float *__restrict__ v_colors, float *__restrict__ v_opacities,
-                     float *__restrict__ v_betas) {
+                     float *__restrict__ v_betas, const float4 *__restrict__ splats, bool splat_colors) {
     constexpr int NG = 7 + CH;           // gradient components per pair
     constexpr bool kSmemAcc = CH <= 4;   // wide colour vectors go straight to global atomics (shared memory budget)
     const uint32_t cam = blockIdx.z;
@@ -132,13 +132,28 @@ rasterize_bwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         if (idx >= range_start) {
             const int32_t g = flatten_ids[idx];
             s_id[tr] = g;
-            const float2 xy = means2d[g];
-            const float4 cn = make_float4(conics[(size_t)g * 3], conics[(size_t)g * 3 + 1], conics[(size_t)g * 3 + 2], 0.f);
-            s_xyob[tr] = make_float4(xy.x, xy.y, opacities[g], betas[g]);
+            float4 xyob, cn;
+            if (splats != nullptr) {  // 48-byte rows of the fused projection kernel (see rasterize_fwd.cu)
+                xyob = splats[(size_t)g * 3];
+                cn = splats[(size_t)g * 3 + 1];
+                cn.w = 0.f;
+            } else {
+                const float2 xy = means2d[g];
+                xyob = make_float4(xy.x, xy.y, opacities[g], betas[g]);
+                cn = make_float4(conics[(size_t)g * 3], conics[(size_t)g * 3 + 1], conics[(size_t)g * 3 + 2], 0.f);
+            }
+            s_xyob[tr] = xyob;
             s_conic[tr] = cn;
-            s_bbox[tr] = support_bbox(xy.x, xy.y, cn.x, cn.y, cn.z);
+            s_bbox[tr] = support_bbox(xyob.x, xyob.y, cn.x, cn.y, cn.z);
+            if (CH == 3 && splats != nullptr && splat_colors) {
+                const float4 c4 = splats[(size_t)g * 3 + 2];
+                s_color[tr * CH + 0] = c4.x;
+                if constexpr (CH > 1) s_color[tr * CH + 1] = c4.y;
+                if constexpr (CH > 2) s_color[tr * CH + 2] = c4.z;
+            } else {
 #pragma unroll
-            for (int k = 0; k < CH; ++k) s_color[tr * CH + k] = colors[(size_t)g * CH + k];
+                for (int k = 0; k < CH; ++k) s_color[tr * CH + k] = colors[(size_t)g * CH + k];
+            }
         }
         __syncthreads();
 
@@ -269,7 +284,7 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
                       const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
                       const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
                       float *__restrict__ v_conics, float *__restrict__ v_colors, float *__restrict__ v_opacities,
-                      float *__restrict__ v_betas) {
+                      float *__restrict__ v_betas, const float4 *__restrict__ splats, bool splat_colors) {
     constexpr int kRec = (int)sizeof(Staged3);  // 48
     const uint32_t cam = blockIdx.z;
     const uint32_t tile_id = blockIdx.y * tile_width + blockIdx.x;
@@ -375,13 +390,28 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
         if (idx >= range_start) {
             const int32_t g = flatten_ids[idx];
             s_id[tr] = g;
-            const float2 xy = means2d[g];
-            const float ca = conics[(size_t)g * 3], cb = conics[(size_t)g * 3 + 1], cc = conics[(size_t)g * 3 + 2];
-            s_rec[tr].xyob = make_float4(xy.x, xy.y, opacities[g], betas[g]);
+            float4 xyob, col;
+            float ca, cb, cc;
+            if (splats != nullptr) {  // 48-byte rows of the fused projection kernel (see rasterize_fwd.cu)
+                xyob = splats[(size_t)g * 3];
+                const float4 cn = splats[(size_t)g * 3 + 1];
+                ca = cn.x, cb = cn.y, cc = cn.z;
+            } else {
+                const float2 xy = means2d[g];
+                xyob = make_float4(xy.x, xy.y, opacities[g], betas[g]);
+                ca = conics[(size_t)g * 3], cb = conics[(size_t)g * 3 + 1], cc = conics[(size_t)g * 3 + 2];
+            }
+            if (splats != nullptr && splat_colors) {
+                col = splats[(size_t)g * 3 + 2];
+                col.w = 0.f;
+            } else {
+                col = make_float4(colors[(size_t)g * 3], colors[(size_t)g * 3 + 1], colors[(size_t)g * 3 + 2], 0.f);
+            }
+            s_rec[tr].xyob = xyob;
             s_rec[tr].conic = make_float4(ca, cb + cb, cc, 0.f);
-            s_rec[tr].col = make_float4(colors[(size_t)g * 3], colors[(size_t)g * 3 + 1], colors[(size_t)g * 3 + 2], 0.f);
-            s_mask[tr] = (uint8_t)refine_sub_tile_mask(sub_tile_mask(support_bbox(xy.x, xy.y, ca, cb, cc), tx0, ty0),
-                                                        xy.x, xy.y, ca, cb, cc, tx0, ty0);
+            s_rec[tr].col = col;
+            s_mask[tr] = (uint8_t)refine_sub_tile_mask(sub_tile_mask(support_bbox(xyob.x, xyob.y, ca, cb, cc), tx0, ty0),
+                                                        xyob.x, xyob.y, ca, cb, cc, tx0, ty0);
         }
         __syncthreads();
 
@@ -464,19 +494,21 @@ int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
                const uint8_t *masks, int width, int height, const int32_t *offsets, const int32_t *flatten_ids,
                const float *render_alphas, const int32_t *last_ids, const float *v_render_colors,
                const float *v_render_alphas, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
-               float *v_betas, cudaStream_t s) {
+               float *v_betas, const float *splats, int splat_colors, cudaStream_t s) {
     const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
     dim3 grid(tw, th, (unsigned)C), block(kTilePixels, 1, 1);
     if constexpr (CH == 3) {
         rasterize_bwd3_kernel<<<grid, block, 0, s>>>(
             C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities, betas, backgrounds, masks,
             (uint32_t)width, (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids,
-            v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas);
+            v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas,
+            (const float4 *)splats, splat_colors != 0);
     } else {
         rasterize_bwd_kernel<CH><<<grid, block, 0, s>>>(
             C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities, betas, backgrounds, masks,
             (uint32_t)width, (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids,
-            v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas);
+            v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas,
+            (const float4 *)splats, splat_colors != 0);
     }
     UBS_LAUNCH_CHECK("rasterize_bwd_kernel");
     return UBS_OK;
@@ -485,28 +517,31 @@ int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
 }  // namespace
 }  // namespace ubs
 
-extern "C" int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
+static int rasterize_bwd_impl(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
                                  const float *means2d, const float *conics, const float *colors,
                                  const float *opacities, const float *betas, const float *backgrounds,
                                  const uint8_t *masks, int channels, int width, int height, int tile_size,
                                  const int32_t *offsets, const int32_t *flatten_ids, const float *render_alphas,
                                  const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
                                  float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
-                                 float *v_betas, void *stream) {
+                                 float *v_betas, const float *splats, int splat_colors, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "rasterize_bwd: bad sizes");
     UBS_CHECK_ARG(tile_size == kTile, "rasterize_bwd: tile_size must be %d (got %d)", kTile, tile_size);
     if (C == 0 || N == 0 || isect_capacity == 0) return UBS_OK;  // no pairs: every gradient stays zero
-    UBS_CHECK_ARG(n_isects && offsets && means2d && conics && colors && opacities && betas && flatten_ids &&
+    UBS_CHECK_ARG(n_isects && offsets && ((means2d && conics && opacities && betas) || splats) &&
+                      (colors || (splats && splat_colors)) && flatten_ids &&
                       render_alphas && last_ids && v_render_colors && v_render_alphas && v_means2d && v_conics &&
                       v_colors && v_opacities && v_betas,
                   "rasterize_bwd: null pointer");
+    UBS_CHECK_ARG(((uintptr_t)splats & 15) == 0, "rasterize_bwd: splats must be 16-byte aligned");
+    UBS_CHECK_ARG(!splat_colors || channels == 3, "rasterize_bwd: splat colours are RGB (channels = %d)", channels);
     cudaStream_t s = (cudaStream_t)stream;
 #define UBS_BWD_CASE(CH)                                                                                               \
     case CH:                                                                                                           \
         return launch_bwd<CH>(C, N, n_isects, isect_capacity, means2d, conics, colors, opacities, betas, backgrounds,  \
                               masks, width, height, offsets, flatten_ids, render_alphas, last_ids, v_render_colors,    \
-                              v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas, s);
+                              v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas, splats, splat_colors, s);
     switch (channels) {
         UBS_BWD_CASE(1)
         UBS_BWD_CASE(2)
@@ -519,4 +554,34 @@ extern "C" int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int6
             return UBS_EUNSUPPORTED;
     }
 #undef UBS_BWD_CASE
+}
+
+extern "C" int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
+                                 const float *means2d, const float *conics, const float *colors,
+                                 const float *opacities, const float *betas, const float *backgrounds,
+                                 const uint8_t *masks, int channels, int width, int height, int tile_size,
+                                 const int32_t *offsets, const int32_t *flatten_ids, const float *render_alphas,
+                                 const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
+                                 float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+                                 float *v_betas, void *stream) {
+    return rasterize_bwd_impl(C, N, n_isects, isect_capacity, means2d, conics, colors, opacities, betas, backgrounds, masks,
+                              channels, width, height, tile_size, offsets, flatten_ids, render_alphas, last_ids,
+                              v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas,
+                              nullptr, 0, stream);
+}
+
+extern "C" int ubs_rasterize_bwd_splats(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
+                                        const float *splats, const float *colors, const float *backgrounds,
+                                        const uint8_t *masks, int channels, int width, int height, int tile_size,
+                                        const int32_t *offsets, const int32_t *flatten_ids,
+                                        const float *render_alphas, const int32_t *last_ids,
+                                        const float *v_render_colors, const float *v_render_alphas, float *v_means2d,
+                                        float *v_conics, float *v_colors, float *v_opacities, float *v_betas,
+                                        void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(splats != nullptr || N == 0 || C == 0 || isect_capacity == 0, "rasterize_bwd_splats: splats is null");
+    return rasterize_bwd_impl(C, N, n_isects, isect_capacity, nullptr, nullptr, colors, nullptr, nullptr, backgrounds, masks,
+                              channels, width, height, tile_size, offsets, flatten_ids, render_alphas, last_ids,
+                              v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas,
+                              splats, colors == nullptr ? 1 : 0, stream);
 }

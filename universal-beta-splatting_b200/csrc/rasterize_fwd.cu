@@ -21,7 +21,8 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
                      const uint8_t *__restrict__ masks, uint32_t width, uint32_t height, uint32_t tile_width,
                      uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
                      const int32_t *__restrict__ flatten_ids, float *__restrict__ render_colors,
-                     float *__restrict__ render_alphas, int32_t *__restrict__ last_ids) {
+                     float *__restrict__ render_alphas, int32_t *__restrict__ last_ids,
+                     const float4 *__restrict__ splats, bool splat_colors) {
     constexpr bool kPacked = CH <= 4;        // colour rides in one float4 of the staged record
     constexpr int kColW = kPacked ? 4 : CH;  // floats of colour per staged pair
     const uint32_t cam = blockIdx.z;
@@ -95,11 +96,28 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         const int32_t idx = range_start + batch * kTilePixels + (int32_t)tr;
         if (idx < range_end) {
             const int32_t g = flatten_ids[idx];
-            const float2 xy = means2d[g];
-            r_xyob = make_float4(xy.x, xy.y, opacities[g], betas[g]);
-            r_conic = make_float4(conics[(size_t)g * 3], conics[(size_t)g * 3 + 1], conics[(size_t)g * 3 + 2], 0.f);
+            if (splats != nullptr) {
+                // one 48-byte row per primitive (written by the fused projection kernel): two sectors per gather
+                // instead of the five of the separate arrays -- the kernel is sensitive to what fits in L1
+                const float4 *sp = splats + (size_t)g * 3;
+                r_xyob = sp[0];
+                r_conic = sp[1];
+                if (CH == 3 && splat_colors) {
+                    const float4 c4 = sp[2];
+                    r_color[0] = c4.x;
+                    if constexpr (CH > 1) r_color[1] = c4.y;
+                    if constexpr (CH > 2) r_color[2] = c4.z;
+                } else {
 #pragma unroll
-            for (int k = 0; k < CH; ++k) r_color[k] = colors[(size_t)g * CH + k];
+                    for (int k = 0; k < CH; ++k) r_color[k] = colors[(size_t)g * CH + k];
+                }
+            } else {
+                const float2 xy = means2d[g];
+                r_xyob = make_float4(xy.x, xy.y, opacities[g], betas[g]);
+                r_conic = make_float4(conics[(size_t)g * 3], conics[(size_t)g * 3 + 1], conics[(size_t)g * 3 + 2], 0.f);
+#pragma unroll
+                for (int k = 0; k < CH; ++k) r_color[k] = colors[(size_t)g * CH + k];
+            }
         }
     };
     if (num_batches > 0) gather(0);
@@ -288,12 +306,14 @@ template <int CH>
 int launch_fwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const float *means2d, const float *conics,
                const float *colors, const float *opacities, const float *betas, const float *backgrounds,
                const uint8_t *masks, int width, int height, const int32_t *offsets, const int32_t *flatten_ids,
-               float *render_colors, float *render_alphas, int32_t *last_ids, cudaStream_t s) {
+               float *render_colors, float *render_alphas, int32_t *last_ids, const float *splats, int splat_colors,
+               cudaStream_t s) {
     const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
     dim3 grid(tw, th, (unsigned)C), block(kTilePixels, 1, 1);
     rasterize_fwd_kernel<CH><<<grid, block, 0, s>>>(C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities,
                                                     betas, backgrounds, masks, (uint32_t)width, (uint32_t)height, tw,
-                                                    th, offsets, flatten_ids, render_colors, render_alphas, last_ids);
+                                                    th, offsets, flatten_ids, render_colors, render_alphas, last_ids,
+                                                    (const float4 *)splats, splat_colors != 0);
     UBS_LAUNCH_CHECK("rasterize_fwd_kernel");
     return UBS_OK;
 }
@@ -301,25 +321,29 @@ int launch_fwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
 }  // namespace
 }  // namespace ubs
 
-extern "C" int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
+static int rasterize_fwd_impl(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
                                  const float *means2d, const float *conics,
                                  const float *colors, const float *opacities, const float *betas,
                                  const float *backgrounds, const uint8_t *masks, int channels, int width, int height,
                                  int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
-                                 float *render_colors, float *render_alphas, int32_t *last_ids, void *stream) {
+                                 float *render_colors, float *render_alphas, int32_t *last_ids, const float *splats,
+                             int splat_colors, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "rasterize_fwd: bad sizes");
     UBS_CHECK_ARG(tile_size == kTile, "rasterize_fwd: tile_size must be %d (got %d)", kTile, tile_size);
     if (C == 0) return UBS_OK;
     UBS_CHECK_ARG(n_isects && offsets && render_colors && render_alphas && last_ids, "rasterize_fwd: null pointer");
-    UBS_CHECK_ARG(N == 0 || (means2d && conics && colors && opacities && betas && (flatten_ids || isect_capacity == 0)),
+    UBS_CHECK_ARG(N == 0 || (((means2d && conics && opacities && betas) || splats) && (colors || (splats && splat_colors)) &&
+                             (flatten_ids || isect_capacity == 0)),
                   "rasterize_fwd: null primitive arrays");
     UBS_CHECK_ARG(C <= 65535, "rasterize_fwd: C=%d exceeds 65535", C);
+    UBS_CHECK_ARG(((uintptr_t)splats & 15) == 0, "rasterize_fwd: splats must be 16-byte aligned");
+    UBS_CHECK_ARG(!splat_colors || channels == 3, "rasterize_fwd: splat colours are RGB (channels = %d)", channels);
     cudaStream_t s = (cudaStream_t)stream;
 #define UBS_FWD_CASE(CH)                                                                                               \
     case CH:                                                                                                           \
         return launch_fwd<CH>(C, N, n_isects, isect_capacity, means2d, conics, colors, opacities, betas, backgrounds, masks, width,    \
-                              height, offsets, flatten_ids, render_colors, render_alphas, last_ids, s);
+                              height, offsets, flatten_ids, render_colors, render_alphas, last_ids, splats, splat_colors, s);
     switch (channels) {
         UBS_FWD_CASE(1)
         UBS_FWD_CASE(2)
@@ -333,6 +357,29 @@ extern "C" int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, int6
             return UBS_EUNSUPPORTED;
     }
 #undef UBS_FWD_CASE
+}
+
+extern "C" int ubs_rasterize_fwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
+                                 const float *means2d, const float *conics,
+                                 const float *colors, const float *opacities, const float *betas,
+                                 const float *backgrounds, const uint8_t *masks, int channels, int width, int height,
+                                 int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
+                                 float *render_colors, float *render_alphas, int32_t *last_ids, void *stream) {
+    return rasterize_fwd_impl(C, N, n_isects, isect_capacity, means2d, conics, colors, opacities, betas, backgrounds, masks,
+                              channels, width, height, tile_size, offsets, flatten_ids, render_colors, render_alphas,
+                              last_ids, nullptr, 0, stream);
+}
+
+extern "C" int ubs_rasterize_fwd_splats(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
+                                        const float *splats, const float *colors, const float *backgrounds,
+                                        const uint8_t *masks, int channels, int width, int height, int tile_size,
+                                        const int32_t *offsets, const int32_t *flatten_ids, float *render_colors,
+                                        float *render_alphas, int32_t *last_ids, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(splats != nullptr || N == 0 || C == 0, "rasterize_fwd_splats: splats is null");
+    return rasterize_fwd_impl(C, N, n_isects, isect_capacity, nullptr, nullptr, colors, nullptr, nullptr, backgrounds, masks,
+                              channels, width, height, tile_size, offsets, flatten_ids, render_colors, render_alphas,
+                              last_ids, splats, colors == nullptr ? 1 : 0, stream);
 }
 
 extern "C" int ubs_rasterize_count(int C, const int64_t *n_isects, int64_t isect_capacity, const float *means2d,

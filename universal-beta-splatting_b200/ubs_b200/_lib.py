@@ -40,11 +40,15 @@ SIGNATURES = {
     "ubs_radix_sort_pairs": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int, c_int, _P, c_size_t, _P]),
     "ubs_rasterize_fwd": (c_int, [c_int, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
                                   _P, _P, _P, _P]),
+    "ubs_rasterize_fwd_splats": (c_int, [c_int, c_int64, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P,
+                                         _P, _P, _P]),
+    "ubs_rasterize_bwd_splats": (c_int, [c_int, c_int64, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_int] +
+                                 [_P] * 12),
     "ubs_rasterize_bwd": (c_int, [c_int, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int] +
                           [_P] * 12),
     "ubs_rasterize_count": (c_int, [c_int, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "ubs_fused_project_fwd": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_float,
-                                      c_float, c_float, c_int, c_int, c_int, c_int] + [_P] * 11 + [c_size_t, _P]),
+                                      c_float, c_float, c_int, c_int, c_int, c_int] + [_P] * 12 + [c_size_t, _P]),
     "ubs_fused_project_bwd": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_int] +
                               [_P] * 10),
     "ubs_l1_ssim_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -97,6 +97,8 @@ class FusedRasterizer:
         self.opacities = torch.empty((C, N), dtype=f32, device=dev)
         self.betas = torch.empty((C, N), dtype=f32, device=dev)
         self.colors = torch.empty((C, N, 3), dtype=f32, device=dev)
+        # the same screen-space record as one 48-byte row per primitive (what the compositing kernels gather from)
+        self.splats = torch.empty((C, N, 12), dtype=f32, device=dev)
         self.tiles_per_gauss = torch.empty((C, N), dtype=i32, device=dev)
         self.n_isects = torch.zeros((1,), dtype=torch.int64, device=dev)
         self.status = torch.zeros((1,), dtype=i32, device=dev)
@@ -183,7 +185,7 @@ class FusedRasterizer:
             C, N, D, ptr(records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), ptr(mask_u8), self.W, self.H,
             self.eps2d, self.near, self.far, self.clip, 1 if self.aa else 0, self.tile_size, self.tw, self.th,
             ptr(self.radii), ptr(self.means2d), ptr(self.depths), ptr(self.conics), ptr(self.opacities),
-            ptr(self.betas), ptr(self.colors), ptr(self.tiles_per_gauss),
+            ptr(self.betas), ptr(self.colors), ptr(self.tiles_per_gauss), ptr(self.splats),
             ptr(self.workspace) if self.sort_mode == "bin" else None, ptr(self.n_isects), ptr(self.workspace),
             self.workspace.numel(), s), "ubs_fused_project_fwd")
         with self._stage("isect_emit_sort_offsets"):
@@ -199,12 +201,10 @@ class FusedRasterizer:
               ptr(self.flatten_ids), ptr(self.offsets), ptr(self.status), ptr(self.workspace),
               self.workspace.numel(), s), "ubs_isect_emit_sort")
         with self._stage("rasterize_fwd"):
-          check(lib.ubs_rasterize_fwd(
-            C, N, ptr(self.n_isects), self.capacity, ptr(self.means2d), ptr(self.conics), ptr(self.colors),
-            ptr(self.opacities),
-            ptr(self.betas), ptr(backgrounds), None, 3, self.W, self.H, self.tile_size, ptr(self.offsets),
-            ptr(self.flatten_ids), ptr(rc_out), ptr(ra_out), ptr(self.last_ids), s),
-            "ubs_rasterize_fwd")
+          check(lib.ubs_rasterize_fwd_splats(
+            C, N, ptr(self.n_isects), self.capacity, ptr(self.splats), None, ptr(backgrounds), None, 3, self.W, self.H,
+            self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(rc_out), ptr(ra_out), ptr(self.last_ids), s),
+            "ubs_rasterize_fwd_splats")
         if self._count_event is None:
             self._host_count[0:1].copy_(self.n_isects, non_blocking=True)
             self._count_event = torch.cuda.Event()
@@ -264,12 +264,11 @@ class FusedRasterizer:
         v_rc, v_ra = v_render_colors.contiguous(), v_render_alphas.contiguous()
         assert v_rc.shape == (C, self.H, self.W, 3) and v_ra.shape == (C, self.H, self.W, 1)
         with self._stage("rasterize_bwd"):
-          check(lib.ubs_rasterize_bwd(
-            C, N, ptr(self.n_isects), self.capacity, ptr(self.means2d), ptr(self.conics), ptr(self.colors),
-            ptr(self.opacities), ptr(self.betas), ptr(backgrounds), None, 3, self.W, self.H, self.tile_size,
-            ptr(self.offsets), ptr(self.flatten_ids), ptr(self.render_alphas), ptr(self.last_ids), ptr(v_rc),
-            ptr(v_ra), ptr(self.v_means2d), ptr(self.v_conics), ptr(self.v_colors), ptr(self.v_opacities),
-            ptr(self.v_betas), s), "ubs_rasterize_bwd")
+          check(lib.ubs_rasterize_bwd_splats(
+            C, N, ptr(self.n_isects), self.capacity, ptr(self.splats), None, ptr(backgrounds), None, 3, self.W, self.H,
+            self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(self.render_alphas), ptr(self.last_ids),
+            ptr(v_rc), ptr(v_ra), ptr(self.v_means2d), ptr(self.v_conics), ptr(self.v_colors), ptr(self.v_opacities),
+            ptr(self.v_betas), s), "ubs_rasterize_bwd_splats")
 
     @torch.no_grad()
     def project_backward_rows(self, records, viewmats, Ks, cam_pos, timestamps, v_records, begin: int, count: int):
