@@ -12,9 +12,13 @@ Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import
   * photometric_loss          train.py:118-121
   * regularisers              train.py:122-124 (note `get_scale[:3]`: the first three primitives)
   * make_adam                 scene/beta_model.py:239-268 -- torch.optim.Adam itself is the oracle of the fused Adam
-  * update_params / relocate / add_new   scene/beta_model.py:548-657 with the sampled indices given
-                              (parity unpinned by reference fixtures: scene/beta_model.py cannot be imported here --
-                              plyfile / fused_ssim / the CUDA extension are missing -- so this is a restatement only)
+  * update_params / relocate / add_new   scene/beta_model.py:548-657 with the sampled indices given.  Pinned by
+                              tests/golden/relocate_D{6,7}.npz = inputs, drawn indices and outputs (parameters and Adam
+                              moments) of the reference's own relocate_gs / add_new_gs, whose source text
+                              tests/golden/make_golden_relocate.py compiles unmodified into a stub class (the module
+                              itself cannot be imported here: plyfile / fused_ssim / the CUDA extension are missing)
+  * sgld_noise                train.py:156-163 on the K1 / K2 restatements of oracle/ubs_oracle.py (pinned by the
+                              _torch_impl fixtures); no reference fixture of its own
 """
 from math import exp
 

@@ -160,6 +160,49 @@ def test_mcmc_relocate_and_add_match_oracle(D):
 
 
 @pytest.mark.parametrize("D", [6, 7])
+def test_mcmc_relocate_and_add_match_reference_fixture(D):
+    """ubs_mcmc_relocate (training.mcmc_relocate / mcmc_add) against the outputs of the reference's own relocate_gs /
+    add_new_gs (tests/golden/relocate_D*.npz, generated by tests/golden/make_golden_relocate.py from the reference
+    source): copied rows bit-exact, rescaled opacity logits within 1e-5, Adam moments bit-exact."""
+    import os
+
+    import numpy as np
+
+    from ubs_b200 import fused, training
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"relocate_D{D}.npz"))
+    names = ("xyz", "mean", "rgb", "opacity", "beta", "scale", "l_triangle")
+
+    def pack(tag, suffix=""):
+        return fused.pack_records(D, *[torch.from_numpy(z[f"{tag}_{n}{suffix}"]).cuda() for n in names])
+
+    rec = pack("in")
+    N = rec.shape[0]
+    adam = training.PackedAdam(D, N)
+    adam.exp_avg.copy_(pack("in", "_m"))
+    adam.exp_avg_sq.copy_(pack("in", "_v"))
+    dead = torch.from_numpy(z["dead_mask"]).nonzero(as_tuple=True)[0].cuda()
+    training.mcmc_relocate(rec, D, dead, torch.from_numpy(z["reinit_idx"]).cuda(), adam)
+
+    def compare(rec_gpu, tag):
+        sl = fused.record_slices(D)
+        want, want_m, want_v = pack(tag), pack(tag, "_m"), pack(tag, "_v")
+        assert rec_gpu.shape == want.shape
+        for n in names:
+            a, b = rec_gpu[:, sl[n]], want[:, sl[n]]
+            if n == "opacity":
+                assert (a - b).abs().max().item() < 1e-5, n
+            else:
+                assert torch.equal(a, b), n
+        assert torch.equal(adam.exp_avg, want_m) and torch.equal(adam.exp_avg_sq, want_v)
+
+    compare(rec, "relocated")
+    rec2 = training.mcmc_add(rec, D, torch.from_numpy(z["add_idx"]).cuda(), adam)
+    assert rec2.shape[0] == N + int(z["n_added"])
+    compare(rec2, "grown")
+
+
+@pytest.mark.parametrize("D", [6, 7])
 def test_sgld_noise_matches_oracle(D):
     """ubs_sgld_noise against the restated train.py:156-163 on the same N(0,1) draw (FP32 tolerance: 1e-5 relative to
     the largest displacement of the row + 1e-7 absolute; every other record column untouched bit for bit)."""

@@ -93,3 +93,45 @@ def test_sgld_noise_oracle_properties():
     want = torch.einsum("nij,nj->ni", cov[:32], noise[:32] * w * 5e5 * 1.6e-4)
     assert torch.allclose(new[:32] - params[0][:32], want, rtol=1e-4, atol=1e-6)
     assert torch.allclose(cov, cov.transpose(1, 2))
+
+
+GROUPS = ("xyz", "mean", "rgb", "opacity", "beta", "scale", "l_triangle")
+
+
+def _load_relocate_fixture(D):
+    z = np.load(os.path.join(os.path.dirname(GOLD), f"relocate_D{D}.npz"))
+
+    def state(tag):
+        params = [torch.from_numpy(z[f"{tag}_{n}"]).clone() for n in GROUPS]
+        moments = [(torch.from_numpy(z[f"{tag}_{n}_m"]).clone(), torch.from_numpy(z[f"{tag}_{n}_v"]).clone()) for n in GROUPS]
+        return params, moments
+
+    return z, state
+
+
+@pytest.mark.parametrize("D", [6, 7])
+def test_relocation_oracle_matches_reference_fixture(D):
+    """oracle/train_oracle.py relocate / add_new against tests/golden/relocate_D*.npz = outputs of the reference's OWN
+    relocate_gs / add_new_gs (scene/beta_model.py:575-657), run on CPU by tests/golden/make_golden_relocate.py with the
+    indices torch.multinomial drew recorded.  Pins the restatement (parameters AND Adam moments)."""
+    from oracle import train_oracle as T
+
+    z, state = _load_relocate_fixture(D)
+    params, moments = state("in")
+    dead = torch.from_numpy(z["dead_mask"]).nonzero(as_tuple=True)[0]
+    reinit = torch.from_numpy(z["reinit_idx"])
+    assert dead.numel() == reinit.numel() > 10 and torch.bincount(reinit).max() >= 2
+    T.relocate(params, moments, dead, reinit)
+    want_p, want_m = state("relocated")
+    for n, p, w in zip(GROUPS, params, want_p):
+        assert torch.allclose(p, w, rtol=1e-6, atol=1e-7), n
+    for n, (m, v), (wm, wv) in zip(GROUPS, moments, want_m):
+        assert torch.equal(m, wm) and torch.equal(v, wv), n
+    add_idx = torch.from_numpy(z["add_idx"])
+    assert add_idx.numel() == int(z["n_added"]) > 0
+    grown, grown_m = T.add_new(params, moments, add_idx)
+    want_p, want_m = state("grown")
+    for n, p, w in zip(GROUPS, grown, want_p):
+        assert p.shape == w.shape and torch.allclose(p, w, rtol=1e-6, atol=1e-7), n
+    for n, (m, v), (wm, wv) in zip(GROUPS, grown_m, want_m):
+        assert torch.equal(m, wm) and torch.equal(v, wv), n
