@@ -17,8 +17,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import
                               moments) of the reference's own relocate_gs / add_new_gs, whose source text
                               tests/golden/make_golden_relocate.py compiles unmodified into a stub class (the module
                               itself cannot be imported here: plyfile / fused_ssim / the CUDA extension are missing)
-  * sgld_noise                train.py:156-163 on the K1 / K2 restatements of oracle/ubs_oracle.py (pinned by the
-                              _torch_impl fixtures); no reference fixture of its own
+  * sgld_noise                train.py:156-163 on the K1 / K2 restatements of oracle/ubs_oracle.py.  Pinned by
+                              tests/golden/sgld_D{6,7}.npz = those four statements of the reference's train.py,
+                              executed unmodified by tests/golden/make_golden_sgld.py
 """
 from math import exp
 

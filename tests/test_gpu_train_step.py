@@ -236,6 +236,29 @@ def test_sgld_noise_matches_oracle(D):
     assert torch.equal(n2, torch.randn((N, 3), device="cuda", generator=gd))
 
 
+@pytest.mark.parametrize("D", [6, 7])
+def test_sgld_noise_matches_reference_fixture(D):
+    """ubs_sgld_noise against tests/golden/sgld_D*.npz (the reference's own train.py:156-163 statements, executed by
+    tests/golden/make_golden_sgld.py): 1e-5 of the displacement + FP32 rounding of the position."""
+    import os
+
+    import numpy as np
+
+    from ubs_b200 import fused, training
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"sgld_D{D}.npz"))
+    N = z["xyz"].shape[0]
+    t = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    rec = fused.pack_records(D, t(z["xyz"]), torch.zeros(N, D - 3, device="cuda"), torch.zeros(N, 3, device="cuda"),
+                             t(z["opacity"]), torch.zeros(N, D - 2, device="cuda"), t(z["scale"]), t(z["l_triangle"]))
+    training.sgld_noise(rec, D, float(z["noise_lr"]), float(z["xyz_lr"]), noise=t(z["noise"]))
+    want, x0 = torch.from_numpy(z["xyz_out"]), torch.from_numpy(z["xyz"])
+    moved = (want - x0).abs()
+    got = rec[:, :3].cpu()
+    assert bool(((got - want).abs() <= 1e-5 * moved.max(dim=1, keepdim=True).values + 2e-7 * x0.abs() + 1e-12).all()), \
+        (got - want).abs().max().item()
+
+
 def test_train_step_reduces_loss_and_matches_manual_composition():
     """TrainStep.step == forward, loss kernel, backward, Adam composed by hand; and it learns."""
     from ubs_b200 import fused, synth, training

@@ -135,3 +135,20 @@ def test_relocation_oracle_matches_reference_fixture(D):
         assert p.shape == w.shape and torch.allclose(p, w, rtol=1e-6, atol=1e-7), n
     for n, (m, v), (wm, wv) in zip(GROUPS, grown_m, want_m):
         assert torch.equal(m, wm) and torch.equal(v, wv), n
+
+
+@pytest.mark.parametrize("D", [6, 7])
+def test_sgld_noise_oracle_matches_reference_fixture(D):
+    """oracle/train_oracle.py sgld_noise against tests/golden/sgld_D*.npz = the reference's own statements of
+    train.py:156-163 executed by tests/golden/make_golden_sgld.py (with its pure-torch K1 / K2 for the covariance)."""
+    from oracle import train_oracle as T
+
+    z = np.load(os.path.join(os.path.dirname(GOLD), f"sgld_D{D}.npz"))
+    N = z["xyz"].shape[0]
+    params = [torch.from_numpy(z["xyz"]), torch.zeros(N, D - 3), torch.zeros(N, 3), torch.from_numpy(z["opacity"]),
+              torch.zeros(N, D - 2), torch.from_numpy(z["scale"]), torch.from_numpy(z["l_triangle"])]
+    got = T.sgld_noise(params, torch.from_numpy(z["noise"]), float(z["noise_lr"]), float(z["xyz_lr"]))
+    want = torch.from_numpy(z["xyz_out"])
+    moved = (want - params[0]).abs()
+    assert moved.max().item() > 1e-7
+    assert bool(((got - want).abs() <= 1e-5 * moved + 1e-7 * params[0].abs() + 1e-12).all())
