@@ -102,8 +102,11 @@ def rasterization(
 
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
+    # tile binning + per-tile depth sort (bit-identical lists, ~2x faster than emit + global radix sort); it needs
+    # non-negative depths, which a positive near plane guarantees for every visible primitive
     tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_tiles(
-        means2d, radii, depths, tile_size, tile_width, tile_height, n_cameras=C, return_offsets=True)
+        means2d, radii, depths, tile_size, tile_width, tile_height, n_cameras=C, return_offsets=True,
+        method="bin" if near_plane > 0 else "onesweep")
     meta.update({"tile_width": tile_width, "tile_height": tile_height, "tiles_per_gauss": tiles_per_gauss,
                  "isect_ids": isect_ids, "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width,
                  "height": height, "tile_size": tile_size, "n_cameras": C})
