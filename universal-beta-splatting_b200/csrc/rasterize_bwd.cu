@@ -308,7 +308,7 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
     if (num_batches <= 0) return;
 
     __shared__ Staged3 s_rec[kTilePixels + 1];  // [kTilePixels] = sentinel (sigma = NaN) padding the lists
-    __shared__ uint8_t s_mask[kTilePixels];  // sub-tiles the sigma < 1 box of each staged pair can touch
+    __shared__ __align__(8) uint8_t s_mask[kTilePixels];  // sub-tiles the sigma < 1 box of each staged pair can touch (0 past the batch)
     __shared__ int32_t s_id[kTilePixels];
     __shared__ float s_acc[kTilePixels * kAccStride];
     __shared__ __align__(8) uint16_t s_list[kTilePixels / 32][kTilePixels + 4];
@@ -412,6 +412,8 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
             s_rec[tr].col = col;
             s_mask[tr] = (uint8_t)refine_sub_tile_mask(sub_tile_mask(support_bbox(xyob.x, xyob.y, ca, cb, cc), tx0, ty0),
                                                         xyob.x, xyob.y, ca, cb, cc, tx0, ty0);
+        } else {
+            s_mask[tr] = 0;
         }
         __syncthreads();
 
@@ -419,13 +421,30 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
         const int32_t t_begin = max(0, batch_end - warp_bin_final);
         const int64_t pmin = inside ? max((int64_t)0, (int64_t)batch_end - bin_final) : (int64_t)kTilePixels + 1;
         const uint32_t off_min = (uint32_t)min(pmin, (int64_t)kTilePixels + 1) * kRec;
-        uint32_t cnt = 0;
-        for (int32_t p0 = t_begin & ~31; p0 < batch_size; p0 += 32) {
-            const int32_t p = p0 + (int32_t)lane;
-            const bool hit = p >= t_begin && p < batch_size && ((s_mask[p] >> warp) & 1u);
-            const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (hit) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(p * kRec);
-            cnt += __popc(m);
+        // lane l takes the eight staged pairs 8 l .. 8 l + 7 (one 64-bit load of their masks); one warp scan of the per-lane
+        // hit counts places them in order (see rasterize_fwd.cu)
+        unsigned long long bits = (*reinterpret_cast<const unsigned long long *>(s_mask + 8 * lane) >> warp) & 0x0101010101010101ull;
+        {
+            const int32_t skip = t_begin - 8 * (int32_t)lane;  // leading pairs of this lane that lie before t_begin
+            if (skip >= 8) bits = 0ull;
+            else if (skip > 0) bits &= ~0ull << (8 * skip);
+        }
+        const uint32_t n_mine = (uint32_t)__popcll(bits);
+        uint32_t incl = n_mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+            if ((int)lane >= off) incl += t;
+        }
+        const uint32_t cnt = __shfl_sync(0xffffffffu, incl, 31);
+        {
+            uint32_t pos = incl - n_mine;
+            const uint32_t lo = (uint32_t)bits, hi = (uint32_t)(bits >> 32);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t word = k < 4 ? lo : hi;
+                if ((word >> (8 * (k & 3))) & 1u) my_list[pos++] = (uint16_t)((8u * lane + (uint32_t)k) * (uint32_t)kRec);
+            }
         }
         if (lane < 3) my_list[cnt + lane] = (uint16_t)(kTilePixels * kRec);  // pad the last triple with the sentinel
         __syncwarp();

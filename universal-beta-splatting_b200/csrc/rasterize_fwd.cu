@@ -63,7 +63,7 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
     };
     constexpr int kUnroll = 4;
     __shared__ Staged s_rec[kTilePixels + 1];  // [kTilePixels] = sentinel whose sigma is NaN (pads the lists)
-    __shared__ uint8_t s_mask[kTilePixels];    // sub-tiles the (inflated) sigma < 1 box of each staged pair can touch
+    __shared__ __align__(8) uint8_t s_mask[kTilePixels];  // sub-tiles the (inflated) sigma < 1 box of each staged pair can touch (0 past the batch)
     // per-warp compacted lists of shared-window ADDRESSES of the staged records (one LDS.128 fetches the four addresses
     // of an unrolled round), padded to a multiple of kUnroll with the sentinel
     __shared__ __align__(16) uint32_t s_list[kTilePixels / 32][kTilePixels + kUnroll];
@@ -126,7 +126,9 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         // everyone has finished reading the previous batch; stop when every pixel of the tile is done
         if (__syncthreads_count(T < 0.f) >= kTilePixels) break;
         s_rec[tr].xyob = r_xyob;
-        s_mask[tr] = (uint8_t)sub_tile_mask(support_bbox(r_xyob.x, r_xyob.y, r_conic.x, r_conic.y, r_conic.z), tx0, ty0);
+        s_mask[tr] = (int32_t)tr < range_end - (range_start + b * kTilePixels)
+                         ? (uint8_t)sub_tile_mask(support_bbox(r_xyob.x, r_xyob.y, r_conic.x, r_conic.y, r_conic.z), tx0, ty0)
+                         : (uint8_t)0;
         s_rec[tr].conic = make_float4(r_conic.x, r_conic.y + r_conic.y, r_conic.z, 0.f);  // b + b as the reference forms it
         if constexpr (kPacked) {
             *reinterpret_cast<float4 *>(s_rec[tr].col) = make_float4(r_color[0], r_color[1], r_color[2], r_color[3]);
@@ -141,14 +143,28 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
         const int32_t batch_size = min((int32_t)kTilePixels, range_end - batch_start);
         if (__all_sync(0xffffffffu, T < 0.f)) continue;  // whole warp finished: nothing to composite
 
-        // warp-level cull: keep (in order) only the pairs whose support touches this warp's 8x4 pixels
-        uint32_t cnt = 0;
-        for (int32_t p0 = 0; p0 < batch_size; p0 += 32) {
-            const int32_t p = p0 + (int32_t)lane;
-            const bool hit = p < batch_size && ((s_mask[p] >> warp) & 1u);
-            const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (hit) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = rec_addr + (uint32_t)p * (uint32_t)sizeof(Staged);
-            cnt += __popc(m);
+        // warp-level cull: keep (in order) only the pairs whose support touches this warp's 8x4 pixels.  Lane l takes the
+        // eight staged pairs 8 l .. 8 l + 7 (one 64-bit load of their masks), one warp scan of the per-lane hit counts
+        // places them: ~50 instructions per 256-pair batch instead of eight ballot rounds of ~29
+        const unsigned long long m8 = *reinterpret_cast<const unsigned long long *>(s_mask + 8 * lane);
+        const unsigned long long bits = (m8 >> warp) & 0x0101010101010101ull;
+        const uint32_t n_mine = (uint32_t)__popcll(bits);
+        uint32_t incl = n_mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+            if ((int)lane >= off) incl += t;
+        }
+        const uint32_t cnt = __shfl_sync(0xffffffffu, incl, 31);
+        {
+            uint32_t pos = incl - n_mine;
+            const uint32_t lo = (uint32_t)bits, hi = (uint32_t)(bits >> 32);
+            const uint32_t first = rec_addr + 8u * lane * (uint32_t)sizeof(Staged);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t word = k < 4 ? lo : hi;
+                if ((word >> (8 * (k & 3))) & 1u) my_list[pos++] = first + (uint32_t)k * (uint32_t)sizeof(Staged);
+            }
         }
         if (lane < kUnroll) my_list[cnt + lane] = rec_addr + (uint32_t)(kTilePixels * sizeof(Staged));
         __syncwarp();
