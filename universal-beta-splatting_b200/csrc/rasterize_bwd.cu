@@ -271,7 +271,8 @@ struct __align__(16) Staged3 {
     float4 conic;  // a, 2b, c, (unused)
     float4 col;    // r, g, b, (unused)
 };
-constexpr int kAccStride = 11;  // 10 accumulators per pair, odd stride -> conflict-free flush
+constexpr int kAccStride = 12;  // 10 accumulators per pair in a 48-byte row: the byte offset of a pair's row equals that of its
+                                // staged record (both 48 p), so the hot loop adds to s_acc + list offset + 4 * component
 
 __global__ void __launch_bounds__(kTilePixels)
 rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev, int64_t isect_capacity,
@@ -310,7 +311,7 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
     __shared__ Staged3 s_rec[kTilePixels + 1];  // [kTilePixels] = sentinel (sigma = NaN) padding the lists
     __shared__ __align__(8) uint8_t s_mask[kTilePixels];  // sub-tiles the sigma < 1 box of each staged pair can touch (0 past the batch)
     __shared__ int32_t s_id[kTilePixels];
-    __shared__ float s_acc[kTilePixels * kAccStride];
+    __shared__ __align__(16) float s_acc[kTilePixels * kAccStride];
     __shared__ __align__(8) uint16_t s_list[kTilePixels / 32][kTilePixels + 4];
 
     const float tx0 = (float)(blockIdx.x * kTile) + 0.5f, ty0 = (float)(blockIdx.y * kTile) + 0.5f;  // first pixel centre
@@ -471,21 +472,20 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
             }
             const uint32_t q = lane / kGrad3, comp = lane - q * kGrad3;
             const uint32_t oq = q == 0 ? o0 : (q == 1 ? o1 : o2);
+            static_assert(kAccStride * sizeof(float) == sizeof(Staged3), "accumulator rows mirror the staged records");
             if (lane < 3 * kGrad3 && oq < (uint32_t)(kTilePixels * kRec) && v[0] != 0.f)
-                atomicAdd(&s_acc[(oq / kRec) * kAccStride + comp], v[0]);
+                atomicAdd(reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(s_acc) + oq) + comp, v[0]);
         }
         __syncthreads();
 
         // flush: one set of global atomics per (tile, pair); finish the moment form here
         if ((int32_t)tr < batch_size) {
-            float *acc = s_acc + tr * kAccStride;
-            float a[kGrad3];
+            float4 *acc = reinterpret_cast<float4 *>(s_acc + tr * kAccStride);  // 48-byte rows: three vector loads
+            const float4 q0 = acc[0], q1 = acc[1], q2 = acc[2];
+            const float a[kGrad3] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
             bool nz = false;
 #pragma unroll
-            for (int k = 0; k < kGrad3; ++k) {
-                a[k] = acc[k];
-                nz |= (a[k] != 0.f);
-            }
+            for (int k = 0; k < kGrad3; ++k) nz |= (a[k] != 0.f);
             if (nz) {
                 const size_t g = (size_t)s_id[tr];
                 const float4 conic = s_rec[tr].conic;  // a, 2b, c
@@ -500,8 +500,7 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
                 atomicAdd(v_means2d + g * 2 + 1, __fmaf_rn(conic.y, a[6], (conic.z + conic.z) * a[7]));
                 atomicAdd(v_opacities + g, a[8]);
                 atomicAdd(v_betas + g, a[9] * 0.693147180559945f);  // lg2 -> ln
-#pragma unroll
-                for (int k = 0; k < kGrad3; ++k) acc[k] = 0.f;
+                acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     }
