@@ -120,7 +120,9 @@ int ubs_projection_bwd(int C, int64_t N, const float *means, const float *covars
  *   ubs_isect_emit_sort(...)   emits (key,val) pairs, stable LSD onesweep sort on bits
  *                              [0, 32+tile_n_bits+cam_n_bits), writes offsets[C,th,tw].
  *                              capacity = size of isect_ids / flatten_ids in elements; if *n_isects exceeds it
- *                              nothing past capacity is written and *status (device int32) gets bit 0 set.
+ *                              nothing past capacity is written.  status (NULL or two device int32): status[0] = 1 if
+ *                              THIS call's list was truncated else 0 (rewritten by every call), status[1] counts the
+ *                              truncated calls.  The projection-backward entry points take status as their skip_flag.
  * key = cam << (32+tb) | tile << 32 | (int64)(int32)float_bits(depth) ; val = cam*N + prim.                  */
 size_t ubs_isect_workspace_bytes(int64_t CN, int64_t capacity);
 int ubs_isect_count(int C, int64_t N, const float *means2d, const int32_t *radii, int tile_size, int tile_width,
@@ -134,7 +136,7 @@ int ubs_isect_emit_sort(int C, int64_t N, const float *means2d, const int32_t *r
                         int64_t capacity, int64_t *isect_ids, /* [capacity] sorted keys out */
                         int32_t *flatten_ids,                 /* [capacity] sorted vals out */
                         int32_t *offsets,                     /* [C,th,tw] or NULL */
-                        int32_t *status,                      /* [1] device or NULL */
+                        int32_t *status,                      /* [2] device or NULL */
                         void *workspace, size_t workspace_bytes, void *stream);
 /* stand-alone offset encoding of already sorted keys (isect_tiles.cu:287-366). n_isects is a host value.     */
 int ubs_isect_offset_encode(int64_t n_isects, const int64_t *isect_ids, int C, int tile_width, int tile_height,
@@ -149,7 +151,7 @@ int ubs_isect_offset_encode(int64_t n_isects, const int64_t *isect_ids, int C, i
  * Requires depths >= +0 for every primitive with radii > 0 (near_plane > 0); otherwise use ubs_isect_emit_sort.
  *   deltas_ready = 1: ubs_fused_project_fwd(tile_delta = workspace) already accumulated the corner deltas
  *   deltas_ready = 0: computed here from means2d / radii (tiles_per_gauss [C,N] is then written if non-NULL)
- * capacity bounds the pair arrays exactly as in ubs_isect_emit_sort (*status bit 0 on overflow; offsets are then
+ * capacity bounds the pair arrays exactly as in ubs_isect_emit_sort (status[0] / status[1] as there; offsets are then
  * clamped to capacity).  No host synchronisation.                                                            */
 size_t ubs_isect_bin_workspace_bytes(int C, int tile_width, int tile_height, int64_t capacity);
 int ubs_isect_bin_sort(int C, int64_t N, const float *means2d, const int32_t *radii, const float *depths,
@@ -159,7 +161,7 @@ int ubs_isect_bin_sort(int C, int64_t N, const float *means2d, const int32_t *ra
                        int64_t *isect_ids,                  /* [capacity] */
                        int32_t *flatten_ids,                /* [capacity] */
                        int32_t *offsets,                    /* [C,th,tw]  */
-                       int32_t *status,                     /* [1] device or NULL */
+                       int32_t *status,                     /* [2] device or NULL */
                        void *workspace, size_t workspace_bytes, void *stream);
 /* stand-alone stable radix sort of (int64 key, int32 val) pairs on bits [begin_bit, end_bit); n on device.   */
 size_t ubs_radix_sort_workspace_bytes(int64_t capacity);
@@ -198,9 +200,12 @@ int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int64_t isect_c
  * counts[8] (device u64) = { E_test, E_acc, E_cull, pairs staged, E_any, E_cull4, E_any4, E_any8x2 } -- see
  * csrc/rasterize_fwd.cu.                                                                                    */
 /* The same two kernels gathering from the 48-byte splat rows ubs_fused_project_fwd writes (two sectors per pair
- * instead of five: the compositing kernels are sensitive to what stays in L1).  colors: NULL = the RGB stored in the
- * rows (channels must be 3), else a [C,N,channels] array as above (depth / feature channels of the viewer modes).
- * The gradient outputs of the backward stay separate arrays (they feed ubs_fused_project_bwd).                 */
+ * instead of five: the compositing kernels are sensitive to what stays in L1).  colors: NULL = colours out of the rows
+ * themselves -- channels 3: RGB; channels 4: RGB + depth (render modes "RGB+D" / "RGB+ED"); channels 1: depth
+ * ("Depth" / "EDepth" / "Normal"; reference: rendering.py:131-142) -- else a [C,N,channels] array as above.
+ * The gradient outputs of the backward stay separate arrays (they feed ubs_fused_project_bwd); with colours out of
+ * the rows and channels 4 or 1, v_colors is [C,N,3] (RGB part) and the depth channel's gradient goes to v_depths [C,N]
+ * (must be given and zeroed by the caller; NULL otherwise).                                                     */
 int ubs_rasterize_fwd_splats(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
                              const float *splats, /* [C,N,12] */
                              const float *colors, const float *backgrounds, const uint8_t *masks, int channels,
@@ -213,7 +218,7 @@ int ubs_rasterize_bwd_splats(int C, int64_t N, const int64_t *n_isects, int64_t 
                              const int32_t *offsets, const int32_t *flatten_ids, const float *render_alphas,
                              const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
                              float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, float *v_betas,
-                             void *stream);
+                             float *v_depths, void *stream);
 int ubs_rasterize_count(int C, const int64_t *n_isects, int64_t isect_capacity, const float *means2d,
                         const float *conics, const float *opacities, const float *betas, int width, int height,
                         int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
@@ -260,6 +265,12 @@ int ubs_fused_project_fwd(int C, int64_t N, int D, const float *records, /* [N, 
                           int64_t *n_isects,        /* [1] device (may be NULL when tile_delta is given) */
                           void *workspace, size_t workspace_bytes, /* ubs_isect_workspace_bytes(C*N, cap); unused
                                                                       when tile_delta is given */
+                          int activated,      /* != 0: the records hold ACTIVATED values (softplus'd scales, sigmoid'd
+                                                 opacity, 4 exp'd betas) -- what ubs_pack_records builds from the
+                                                 tensors the reference's operator chain passes around */
+                          const float *query, /* NULL, or [N, D-3]: the conditioning query of every primitive as the
+                                                 caller computed it (scene/beta_model.py:675-690), used for every
+                                                 camera instead of the view direction from cam_pos [+ timestamp] */
                           void *stream);
 /* backward of the above: consumes gradients w.r.t. the screen-space records and writes a packed gradient
  * record buffer (same layout as `records`; accumulated over cameras; zeroed by callee).                      */
@@ -269,7 +280,20 @@ int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const f
                           const float *v_means2d, const float *v_depths, const float *v_conics,
                           const float *v_opacities, const float *v_betas, const float *v_colors, /* [C,N,3] or NULL */
                           float *v_records,                                                       /* [N, stride] */
+                          int activated, const float *query, /* as in ubs_fused_project_fwd */
+                          const int32_t *skip_flag, /* NULL, or the `status` of the frame's tile-list build: when
+                                                       status[0] != 0 (the frame lost pairs to the capacity bound) the
+                                                       gradient records are all zero -- the view is dropped */
                           void *stream);
+
+/* Packing of the reference's separate per-primitive tensors into records and back (the zero-edit drop-in route,
+ * ubs_b200/dropin.py; csrc/pack.cu).  mean [N,D] = xyz | conditional mean (get_mean, scene/beta_model.py:111-113),
+ * rgb [N,3], opacity [N], beta0 [N] (spatial beta), beta_c [N,D-3], scale [N,D], l_triangle [N,D(D-1)/2]; values are
+ * copied as they are (activated or raw).  ubs_unpack_records: any destination may be NULL (gradient not wanted).  */
+int ubs_pack_records(int64_t N, int D, const float *mean, const float *rgb, const float *opacity, const float *beta0,
+                     const float *beta_c, const float *scale, const float *l_triangle, float *records, void *stream);
+int ubs_unpack_records(int64_t N, int D, const float *records, float *mean, float *rgb, float *opacity, float *beta0,
+                       float *beta_c, float *scale, float *l_triangle, void *stream);
 
 /* ---- the train step around the render --------------------------------------------- */
 /* Photometric loss and its gradient: (1 - lambda) * mean|img - gt| + lambda * (1 - mean SSIM(img, gt)).
@@ -304,7 +328,10 @@ int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *records, const fl
                                const float *v_means2d, const float *v_depths, const float *v_conics,
                                const float *v_opacities, const float *v_betas, const float *v_colors, float *exp_avg,
                                float *exp_avg_sq, const double *h_lr, double beta1, double beta2, double eps,
-                               int64_t step, double opacity_reg, double scale_reg, void *stream);
+                               int64_t step, double opacity_reg, double scale_reg,
+                               const int32_t *skip_flag, /* as above; a truncated frame leaves records and moments
+                                                            untouched */
+                               void *stream);
 
 /* ---- sharded train step over the GPUs of one NVSwitch box (no reference counterpart: SURVEY.md 2.3) ------------ */
 /* Rows are split into `world` shards of `shard_rows` (a multiple of 128) rows; rank g owns shard g, i.e. its Adam
@@ -321,7 +348,9 @@ int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *records, const 
                                   int calc_compensations, const int32_t *radii, const float *conics,
                                   const float *v_means2d, const float *v_depths, const float *v_conics,
                                   const float *v_opacities, const float *v_betas, const float *v_colors, int world,
-                                  int rank, int64_t shard_rows, float *const *h_staging, void *stream);
+                                  int rank, int64_t shard_rows, float *const *h_staging,
+                                  const int32_t *skip_flag, /* as in ubs_fused_project_bwd: zero tiles are sent */
+                                  void *stream);
 int ubs_reduce_adam_gather(int64_t N, int D, int world, int rank, int64_t shard_rows, const float *staging,
                            float *exp_avg_shard, float *exp_avg_sq_shard, float *const *h_peer_records,
                            float *mc_records, /* NULL, or the NVLS multicast address of the records buffers: one

@@ -59,7 +59,14 @@ def _forward_parity(ref, scene, cam, bg, rz, rec):
     n_ref = R["isect_ids"].numel()
     # torch's softplus / sigmoid / exp feed the reference chain, fast-math intrinsics the fused kernel: radii may
     # differ for a handful of primitives whose footprint sits on an integer boundary
-    assert (rz.radii == R["radii"]).float().mean().item() > 0.999
+    # -- counted and bounded by count, not by rate: at most 1 primitive in 2000 may land on the other side of an integer
+    # boundary (the zero-edit drop-in route, which feeds the kernels torch's own activations, has none:
+    # tests/test_gpu_dropin.py)
+    n_radii_bad = int((rz.radii != R["radii"]).sum())
+    n_vis_flip = int(((rz.radii > 0) != (R["radii"] > 0)).sum())
+    print("radii differ for %d of %d primitives (%d change visibility); pairs %d vs %d (reference)"
+          % (n_radii_bad, rz.radii.numel(), n_vis_flip, n, n_ref))
+    assert n_radii_bad <= max(4, rz.radii.numel() // 2000), n_radii_bad
     assert abs(n - n_ref) <= max(4, n_ref // 1000), (n, n_ref)
     torch.testing.assert_close(ra, R["render_alphas"], rtol=0, atol=IMG_ATOL)
     torch.testing.assert_close(rc, R["render_colors"], rtol=0, atol=IMG_ATOL)

@@ -189,7 +189,7 @@ __device__ void bin_offsets_of_camera(uint32_t cam, uint32_t C, uint32_t n_tiles
     }
     if (cam == C - 1 && threadIdx.x == 0) {
         *n_isects = base;
-        if (base > capacity && status != nullptr) atomicOr(status, 1);
+        report_truncation(status, base > capacity);
     }
 }
 
@@ -210,7 +210,7 @@ __device__ void bin_offsets_from_smem(const int32_t *cnt, uint32_t n_tiles, int6
     }
     if (threadIdx.x == 0) {
         *n_isects = total;
-        if (total > capacity && status != nullptr) atomicOr(status, 1);
+        report_truncation(status, total > capacity);
     }
 }
 

@@ -63,8 +63,10 @@ struct PrimState {
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// `activated`: the record already holds the ACTIVATED values (softplus'd scales, sigmoid'd opacity, 4 exp'd betas), as
+// the reference's operator chain sees them (scene/beta_model.py:103-121) -- the zero-edit drop-in route packs those.
 template <int D>
-__device__ __forceinline__ void decode_record(const float *rec, PrimState<D> &ps) {
+__device__ __forceinline__ void decode_record(const float *rec, PrimState<D> &ps, bool activated) {
     constexpr int C = D - 3, M = NdDims<D>::M;
     // layout (ubs_b200.h): xyz | mean | rgb | opacity | beta(D-2) | scale(D) | l_triangle(M)
 #pragma unroll
@@ -73,13 +75,13 @@ __device__ __forceinline__ void decode_record(const float *rec, PrimState<D> &ps
     for (int k = 0; k < C; ++k) ps.mu2[k] = rec[3 + k];
 #pragma unroll
     for (int k = 0; k < 3; ++k) ps.rgb[k] = rec[D + k];
-    ps.opacity = sigmoid_f(rec[D + 3]);
-    ps.beta0 = beta_act_f(rec[D + 4]);
+    ps.opacity = activated ? rec[D + 3] : sigmoid_f(rec[D + 3]);
+    ps.beta0 = activated ? rec[D + 4] : beta_act_f(rec[D + 4]);
 #pragma unroll
-    for (int k = 0; k < C; ++k) ps.beta_c[k] = beta_act_f(rec[D + 5 + k]);
+    for (int k = 0; k < C; ++k) ps.beta_c[k] = activated ? rec[D + 5 + k] : beta_act_f(rec[D + 5 + k]);
     float s[D], lt[M];
 #pragma unroll
-    for (int k = 0; k < D; ++k) s[k] = softplus_f(rec[2 * D + 2 + k]);
+    for (int k = 0; k < D; ++k) s[k] = activated ? rec[2 * D + 2 + k] : softplus_f(rec[2 * D + 2 + k]);
 #pragma unroll
     for (int k = 0; k < M; ++k) lt[k] = rec[3 * D + 2 + k];
     const float R[9] = {1.f, lt[0], lt[1], -lt[0], 1.f, lt[2], -lt[1], -lt[2], 1.f};  // K1: I + skew
@@ -114,7 +116,8 @@ fused_project_fwd_kernel(int C, int64_t N, const float *__restrict__ records, co
                          int32_t *__restrict__ radii, float *__restrict__ means2d, float *__restrict__ depths,
                          float *__restrict__ conics, float *__restrict__ opacities, float *__restrict__ betas,
                          float *__restrict__ colors, int32_t *__restrict__ tiles_per_gauss,
-                         float4 *__restrict__ splats, int32_t *__restrict__ tile_delta) {
+                         float4 *__restrict__ splats, int32_t *__restrict__ tile_delta, int activated,
+                         const float *__restrict__ query) {
     constexpr int Cd = D - 3;
     constexpr int STRIDE = UBS_RECORD_STRIDE(D);
     __shared__ __align__(128) float s_rec[kFusedThreads * STRIDE];
@@ -142,7 +145,14 @@ fused_project_fwd_kernel(int C, int64_t N, const float *__restrict__ records, co
             const float4 v = src[k];
             rec[4 * k + 0] = v.x, rec[4 * k + 1] = v.y, rec[4 * k + 2] = v.z, rec[4 * k + 3] = v.w;
         }
-        decode_record<D>(rec, ps);
+        decode_record<D>(rec, ps, activated != 0);
+    }
+    // query given by the caller (the drop-in route: scene/beta_model.py:675-690 builds it with torch): one row per
+    // primitive, the same for every camera
+    float xq[Cd];
+    if (query != nullptr && active) {
+#pragma unroll
+        for (int k = 0; k < Cd; ++k) xq[k] = query[gid * Cd + k] - ps.mu2[k];
     }
 
     for (int cid = blockIdx.y; cid < C; cid += gridDim.y) {
@@ -156,7 +166,10 @@ fused_project_fwd_kernel(int C, int64_t N, const float *__restrict__ records, co
             const Cam cam = load_cam(viewmats + cid * 16, Ks + cid * 9);
             // query: unit view direction (+ timestamp)   (scene/beta_model.py:675-690)
             float x[Cd];
-            {
+            if (query != nullptr) {
+#pragma unroll
+                for (int k = 0; k < Cd; ++k) x[k] = xq[k];
+            } else {
                 const float dx = ps.xyz[0] - cam_pos[cid * 3 + 0], dy = ps.xyz[1] - cam_pos[cid * 3 + 1],
                             dz = ps.xyz[2] - cam_pos[cid * 3 + 2];
                 const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
@@ -204,7 +217,7 @@ fused_project_fwd_kernel(int C, int64_t N, const float *__restrict__ records, co
             float4 *sp = splats + idx * 3;
             sp[0] = make_float4(o.mean2d[0], o.mean2d[1], opac, ps.beta0);
             sp[1] = make_float4(o.conic[0], o.conic[1], o.conic[2], o.depth);
-            sp[2] = make_float4(ps.rgb[0], ps.rgb[1], ps.rgb[2], 0.f);
+            sp[2] = make_float4(ps.rgb[0], ps.rgb[1], ps.rgb[2], o.depth);  // .w: the 4th colour channel of "RGB+D"
         }
     }
 }
@@ -235,6 +248,13 @@ struct ScatterDst {
     int rank;
 };
 
+// Options shared by the three entry points of the backward kernel.
+struct BwdOpts {
+    int activated;             // records hold activated values (see decode_record): no activation derivative
+    const float *query;        // NULL, or [N, D-3] queries given by the caller instead of the view direction
+    const int32_t *skip_flag;  // NULL, or the `status` word of the frame's tile-list build
+};
+
 // Backward of fused_project_fwd_kernel: one thread per primitive, looping over cameras, so the per-primitive sums
 // need no atomics.  Recomputes the cheap forward intermediates from the record instead of storing them.
 //
@@ -253,8 +273,14 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
                          const float *__restrict__ v_conics, const float *__restrict__ v_opacities,
                          const float *__restrict__ v_betas, const float *__restrict__ v_colors,
                          float *__restrict__ v_records, float *__restrict__ exp_avg,
-                         float *__restrict__ exp_avg_sq, const AdamParams adam, const ScatterDst scatter) {
+                         float *__restrict__ exp_avg_sq, const AdamParams adam, const ScatterDst scatter,
+                         const BwdOpts opts) {
     constexpr int Cd = D - 3, M = NdDims<D>::M;
+    // the frame this gradient belongs to lost pairs to the capacity bound (isect.cuh: report_truncation): with ADAM the
+    // update is not applied at all, otherwise the view contributes a zero gradient (it is dropped from the batch)
+    const bool skip = opts.skip_flag != nullptr && *opts.skip_flag != 0;
+    if (ADAM && skip) return;
+    const bool activated = opts.activated != 0;
     constexpr int STRIDE = UBS_RECORD_STRIDE(D);
     extern __shared__ __align__(128) float s_tiles[];  // [records][exp_avg][exp_avg_sq] (the last two with ADAM)
     float *const s_rec = s_tiles;
@@ -291,7 +317,7 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
         bool vis = false;
         if (threadIdx.x < n_here) {
             int cid = 0;
-            for (; cid < C && !vis; ++cid) vis = radii[(int64_t)cid * N + base + threadIdx.x] > 0;
+            for (; cid < C && !vis && !skip; ++cid) vis = radii[(int64_t)cid * N + base + threadIdx.x] > 0;
             if (vis) {
                 // The screen-space record and its gradients are gathered per visible row far below, behind the bulk-copy
                 // wait and the forward recompute; start those lines towards L1 now (first camera that sees the row).
@@ -351,12 +377,12 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
         for (int k = 0; k < 3; ++k) xyz[k] = rec[k];
 #pragma unroll
         for (int k = 0; k < Cd; ++k) mu2[k] = rec[3 + k];
-        const float o_in = sigmoid_f(rec[D + 3]);
-        const float beta0 = beta_act_f(rec[D + 4]);
+        const float o_in = activated ? rec[D + 3] : sigmoid_f(rec[D + 3]);
+        const float beta0 = activated ? rec[D + 4] : beta_act_f(rec[D + 4]);
 #pragma unroll
-        for (int k = 0; k < Cd; ++k) beta_c[k] = beta_act_f(rec[D + 5 + k]);
+        for (int k = 0; k < Cd; ++k) beta_c[k] = activated ? rec[D + 5 + k] : beta_act_f(rec[D + 5 + k]);
 #pragma unroll
-        for (int k = 0; k < D; ++k) s[k] = softplus_f(rec[2 * D + 2 + k]);
+        for (int k = 0; k < D; ++k) s[k] = activated ? rec[2 * D + 2 + k] : softplus_f(rec[2 * D + 2 + k]);
 #pragma unroll
         for (int k = 0; k < M; ++k) lt[k] = rec[3 * D + 2 + k];
         const float R[9] = {1.f, lt[0], lt[1], -lt[0], 1.f, lt[2], -lt[1], -lt[2], 1.f};
@@ -397,7 +423,10 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
             if (radii[idx] <= 0) continue;
             const Cam cam = load_cam(viewmats + cid * 16, Ks + cid * 9);
             float x[Cd];
-            {
+            if (opts.query != nullptr) {
+#pragma unroll
+                for (int k = 0; k < Cd; ++k) x[k] = opts.query[gid * Cd + k] - mu2[k];
+            } else {
                 const float dx = xyz[0] - cam_pos[cid * 3 + 0], dy = xyz[1] - cam_pos[cid * 3 + 1],
                             dz = xyz[2] - cam_pos[cid * 3 + 2];
                 const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
@@ -471,14 +500,14 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
         for (int k = 0; k < D; ++k) grad[k] = g_mu[k];  // xyz | mean (no gradient through the view direction)
 #pragma unroll
         for (int k = 0; k < 3; ++k) grad[D + k] = g_rgb[k];
-        grad[D + 3] = g_o * o_in * (1.f - o_in);  // sigmoid'
-        grad[D + 4] = g_beta0 * beta0;             // d(4 e^x)/dx = 4 e^x
+        grad[D + 3] = activated ? g_o : g_o * o_in * (1.f - o_in);  // sigmoid'
+        grad[D + 4] = activated ? g_beta0 : g_beta0 * beta0;         // d(4 e^x)/dx = 4 e^x
 #pragma unroll
-        for (int k = 0; k < Cd; ++k) grad[D + 5 + k] = g_beta_c[k] * beta_c[k];
+        for (int k = 0; k < Cd; ++k) grad[D + 5 + k] = activated ? g_beta_c[k] : g_beta_c[k] * beta_c[k];
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             const float raw = rec[2 * D + 2 + k];
-            grad[2 * D + 2 + k] = vs[k] * (raw > 20.f ? 1.f : sigmoid_f(raw));  // softplus'
+            grad[2 * D + 2 + k] = activated ? vs[k] : vs[k] * (raw > 20.f ? 1.f : sigmoid_f(raw));  // softplus'
         }
 #pragma unroll
         for (int k = 0; k < M; ++k) grad[3 * D + 2 + k] = vlt[k];
@@ -568,7 +597,8 @@ extern "C" int ubs_fused_project_fwd(int C, int64_t N, int D, const float *recor
                                      int tile_width, int tile_height, int32_t *radii, float *means2d, float *depths,
                                      float *conics, float *opacities, float *betas, float *colors,
                                      int32_t *tiles_per_gauss, float *splats, int32_t *tile_delta, int64_t *n_isects,
-                                     void *workspace, size_t workspace_bytes, void *stream) {
+                                     void *workspace, size_t workspace_bytes, int activated, const float *query,
+                                     void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0 && tile_size > 0, "fused_project_fwd: bad sizes");
     UBS_CHECK_ARG(((uintptr_t)splats & 15) == 0, "fused_project_fwd: splats must be 16-byte aligned");
@@ -584,10 +614,10 @@ extern "C" int ubs_fused_project_fwd(int C, int64_t N, int D, const float *recor
         if (n_isects != nullptr) UBS_CUDA_TRY(cudaMemsetAsync(n_isects, 0, sizeof(int64_t), s));
         return UBS_OK;
     }
-    UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && means2d && depths && conics && opacities && betas &&
-                      tiles_per_gauss && (workspace || tile_delta),
+    UBS_CHECK_ARG(records && viewmats && Ks && (cam_pos || query) && radii && means2d && depths && conics && opacities &&
+                      betas && tiles_per_gauss && (workspace || tile_delta),
                   "fused_project_fwd: null pointer");
-    UBS_CHECK_ARG(D != 7 || timestamps != nullptr, "fused_project_fwd: D=7 needs timestamps");
+    UBS_CHECK_ARG(D != 7 || timestamps != nullptr || query != nullptr, "fused_project_fwd: D=7 needs timestamps");
     UBS_CHECK_ARG(((uintptr_t)records & 15) == 0, "fused_project_fwd: records must be 16-byte aligned");
     UBS_CHECK_ARG(CN < ((int64_t)1 << 31), "fused_project_fwd: C*N must fit int32 flatten ids");
     if (tile_delta == nullptr && workspace_bytes < ubs_isect_workspace_bytes(CN, 0)) {
@@ -607,7 +637,7 @@ extern "C" int ubs_fused_project_fwd(int C, int64_t N, int D, const float *recor
         C, N, records, viewmats, Ks, cam_pos, timestamps, prim_mask, (uint32_t)width, (uint32_t)height, eps2d,         \
         near_plane, far_plane, radius_clip, calc_compensations, (uint32_t)tile_size, (uint32_t)tile_width,             \
         (uint32_t)tile_height, radii, means2d, depths, conics, opacities, betas, colors, tiles_per_gauss,             \
-        (float4 *)splats, tile_delta)
+        (float4 *)splats, tile_delta, activated, query)
     if (D == 6) UBS_FUSED_LAUNCH(6);
     else UBS_FUSED_LAUNCH(7);
 #undef UBS_FUSED_LAUNCH
@@ -621,15 +651,16 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
                                      int height, float eps2d, int calc_compensations, const int32_t *radii,
                                      const float *conics, const float *v_means2d, const float *v_depths,
                                      const float *v_conics, const float *v_opacities, const float *v_betas,
-                                     const float *v_colors, float *v_records, void *stream) {
+                                     const float *v_colors, float *v_records, int activated, const float *query,
+                                     const int32_t *skip_flag, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "fused_project_bwd: bad sizes");
     UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd: D must be 6 or 7 (got %d)", D);
     if (N == 0) return UBS_OK;
-    UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && conics && v_means2d && v_conics && v_opacities &&
-                      v_betas && v_records,
+    UBS_CHECK_ARG(records && viewmats && Ks && (cam_pos || query) && radii && conics && v_means2d && v_conics &&
+                      v_opacities && v_betas && v_records,
                   "fused_project_bwd: null pointer");
-    UBS_CHECK_ARG(D != 7 || timestamps != nullptr, "fused_project_bwd: D=7 needs timestamps");
+    UBS_CHECK_ARG(D != 7 || timestamps != nullptr || query != nullptr, "fused_project_bwd: D=7 needs timestamps");
     UBS_CHECK_ARG((((uintptr_t)records | (uintptr_t)v_records) & 15) == 0,
                   "fused_project_bwd: records / v_records must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
@@ -639,16 +670,17 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
     const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams unused{};
     const ScatterDst no_scatter{};
+    const BwdOpts opts{activated, query, skip_flag};
     if (D == 6)
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records,
-            nullptr, nullptr, unused, no_scatter);
+            nullptr, nullptr, unused, no_scatter, opts);
     else
         fused_project_bwd_kernel<7, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records,
-            nullptr, nullptr, unused, no_scatter);
+            nullptr, nullptr, unused, no_scatter, opts);
     UBS_LAUNCH_CHECK("fused_project_bwd_kernel");
     return UBS_OK;
 }
@@ -660,7 +692,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
                                           const float *v_conics, const float *v_opacities, const float *v_betas,
                                           const float *v_colors, float *exp_avg, float *exp_avg_sq, const double *h_lr,
                                           double beta1, double beta2, double eps, int64_t step, double opacity_reg,
-                                          double scale_reg, void *stream) {
+                                          double scale_reg, const int32_t *skip_flag, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "fused_project_bwd_adam: bad sizes");
     UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd_adam: D must be 6 or 7 (got %d)", D);
@@ -676,6 +708,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
     const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
     const size_t smem = (size_t)3 * kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
+    const BwdOpts opts{0, nullptr, skip_flag};
     if (D == 6) {
         UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<6, 3, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -684,7 +717,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
         fused_project_bwd_kernel<6, 3, true><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
-            exp_avg, exp_avg_sq, a, ScatterDst{});
+            exp_avg, exp_avg_sq, a, ScatterDst{}, opts);
     } else {
         UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<7, 3, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -693,7 +726,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
         fused_project_bwd_kernel<7, 3, true><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
-            exp_avg, exp_avg_sq, a, ScatterDst{});
+            exp_avg, exp_avg_sq, a, ScatterDst{}, opts);
     }
     UBS_LAUNCH_CHECK("fused_project_bwd_adam_kernel");
     return UBS_OK;
@@ -705,7 +738,8 @@ extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *reco
                                              const int32_t *radii, const float *conics, const float *v_means2d,
                                              const float *v_depths, const float *v_conics, const float *v_opacities,
                                              const float *v_betas, const float *v_colors, int world, int rank,
-                                             int64_t shard_rows, float *const *h_staging, void *stream) {
+                                             int64_t shard_rows, float *const *h_staging, const int32_t *skip_flag,
+                                             void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(N >= 0 && width > 0 && height > 0, "fused_project_bwd_scatter: bad sizes");
     UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd_scatter: D must be 6 or 7 (got %d)", D);
@@ -730,16 +764,17 @@ extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *reco
     const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
     const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams unused{};
+    const BwdOpts opts{0, nullptr, skip_flag};
     if (D == 6)
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             1, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
-            nullptr, nullptr, unused, sc);
+            nullptr, nullptr, unused, sc, opts);
     else
         fused_project_bwd_kernel<7, 3, false><<<gx, kFusedThreads, smem, s>>>(
             1, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
-            nullptr, nullptr, unused, sc);
+            nullptr, nullptr, unused, sc, opts);
     UBS_LAUNCH_CHECK("fused_project_bwd_scatter_kernel");
     return UBS_OK;
 }

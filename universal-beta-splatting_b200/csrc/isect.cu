@@ -115,10 +115,8 @@ isect_offsets_kernel(const int64_t *__restrict__ n_dev, int64_t n_host, int64_t 
                      int32_t *__restrict__ offsets, int32_t *__restrict__ status) {
     int64_t n = n_dev != nullptr ? *n_dev : n_host;
     const int64_t tile_mask = ((int64_t)1 << tile_n_bits) - 1;
-    if (n > capacity) {
-        if (status != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, 1);
-        n = capacity;
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) report_truncation(status, n > capacity);
+    if (n > capacity) n = capacity;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n == 0) {

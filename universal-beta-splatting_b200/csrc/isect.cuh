@@ -7,6 +7,15 @@ namespace ubs {
 
 constexpr int kIsectThreads = 256;
 
+// Truncation report of the capacity-bounded pair list (one thread per call): status[0] = was THIS call's list
+// truncated (rewritten by every call, so it always describes the most recent frame), status[1] = number of truncated
+// calls so far.  The Adam kernels read status[0] as their skip flag: a truncated frame never updates the parameters.
+__device__ __forceinline__ void report_truncation(int32_t *status, bool truncated) {
+    if (status == nullptr) return;
+    status[0] = truncated ? 1 : 0;
+    if (truncated) atomicAdd(status + 1, 1);
+}
+
 struct TileRect {
     uint32_t x0, y0, x1, y1;  // min inclusive, max exclusive
 };

@@ -29,7 +29,8 @@ rasterize_bwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
                      const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
                      const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
                      float *__restrict__ v_conics, float *__restrict__ v_colors, float *__restrict__ v_opacities,
-                     float *__restrict__ v_betas, const float4 *__restrict__ splats, bool splat_colors) {
+                     float *__restrict__ v_betas, const float4 *__restrict__ splats, bool splat_colors,
+                     float *__restrict__ v_depths) {
     constexpr int NG = 7 + CH;           // gradient components per pair
     constexpr bool kSmemAcc = CH <= 4;   // wide colour vectors go straight to global atomics (shared memory budget)
     const uint32_t cam = blockIdx.z;
@@ -145,11 +146,16 @@ rasterize_bwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
             s_xyob[tr] = xyob;
             s_conic[tr] = cn;
             s_bbox[tr] = support_bbox(xyob.x, xyob.y, cn.x, cn.y, cn.z);
-            if (CH == 3 && splats != nullptr && splat_colors) {
-                const float4 c4 = splats[(size_t)g * 3 + 2];
-                s_color[tr * CH + 0] = c4.x;
-                if constexpr (CH > 1) s_color[tr * CH + 1] = c4.y;
-                if constexpr (CH > 2) s_color[tr * CH + 2] = c4.z;
+            if ((CH == 1 || CH == 3 || CH == 4) && splats != nullptr && splat_colors) {
+                if constexpr (CH == 1) {
+                    s_color[tr] = splats[(size_t)g * 3 + 1].w;  // depth as the colour (rasterize_fwd.cu)
+                } else {
+                    const float4 c4 = splats[(size_t)g * 3 + 2];
+                    s_color[tr * CH + 0] = c4.x;
+                    if constexpr (CH > 1) s_color[tr * CH + 1] = c4.y;
+                    if constexpr (CH > 2) s_color[tr * CH + 2] = c4.z;
+                    if constexpr (CH > 3) s_color[tr * CH + 3] = c4.w;
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < CH; ++k) s_color[tr * CH + k] = colors[(size_t)g * CH + k];
@@ -240,8 +246,16 @@ rasterize_bwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
 #pragma unroll
             for (int k = 0; k < NG; ++k) nz |= (acc[k] != 0.f);
             if (nz) {
+                if (v_depths != nullptr) {
+                    // colours came out of the splat rows: the RGB part goes to v_colors [C,N,3], the depth channel
+                    // (the last one) to v_depths [C,N] -- the two arrays ubs_fused_project_bwd consumes
 #pragma unroll
-                for (int k = 0; k < CH; ++k) atomicAdd(v_colors + (size_t)g * CH + k, acc[k]);
+                    for (int k = 0; k < CH - 1; ++k) atomicAdd(v_colors + (size_t)g * 3 + k, acc[k]);
+                    atomicAdd(v_depths + g, acc[CH - 1]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) atomicAdd(v_colors + (size_t)g * CH + k, acc[k]);
+                }
                 atomicAdd(v_conics + (size_t)g * 3 + 0, acc[CH + 0]);
                 atomicAdd(v_conics + (size_t)g * 3 + 1, acc[CH + 1]);
                 atomicAdd(v_conics + (size_t)g * 3 + 2, acc[CH + 2]);
@@ -512,7 +526,7 @@ int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
                const uint8_t *masks, int width, int height, const int32_t *offsets, const int32_t *flatten_ids,
                const float *render_alphas, const int32_t *last_ids, const float *v_render_colors,
                const float *v_render_alphas, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
-               float *v_betas, const float *splats, int splat_colors, cudaStream_t s) {
+               float *v_betas, const float *splats, int splat_colors, float *v_depths, cudaStream_t s) {
     const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
     dim3 grid(tw, th, (unsigned)C), block(kTilePixels, 1, 1);
     if constexpr (CH == 3) {
@@ -526,7 +540,7 @@ int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
             C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities, betas, backgrounds, masks,
             (uint32_t)width, (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids,
             v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas,
-            (const float4 *)splats, splat_colors != 0);
+            (const float4 *)splats, splat_colors != 0, v_depths);
     }
     UBS_LAUNCH_CHECK("rasterize_bwd_kernel");
     return UBS_OK;
@@ -542,7 +556,7 @@ static int rasterize_bwd_impl(int C, int64_t N, const int64_t *n_isects, int64_t
                                  const int32_t *offsets, const int32_t *flatten_ids, const float *render_alphas,
                                  const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
                                  float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
-                                 float *v_betas, const float *splats, int splat_colors, void *stream) {
+                                 float *v_betas, const float *splats, int splat_colors, float *v_depths, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "rasterize_bwd: bad sizes");
     UBS_CHECK_ARG(tile_size == kTile, "rasterize_bwd: tile_size must be %d (got %d)", kTile, tile_size);
@@ -553,13 +567,17 @@ static int rasterize_bwd_impl(int C, int64_t N, const int64_t *n_isects, int64_t
                       v_colors && v_opacities && v_betas,
                   "rasterize_bwd: null pointer");
     UBS_CHECK_ARG(((uintptr_t)splats & 15) == 0, "rasterize_bwd: splats must be 16-byte aligned");
-    UBS_CHECK_ARG(!splat_colors || channels == 3, "rasterize_bwd: splat colours are RGB (channels = %d)", channels);
+    UBS_CHECK_ARG(!splat_colors || channels == 3 || ((channels == 4 || channels == 1) && v_depths != nullptr),
+                  "rasterize_bwd: splat colours are RGB, or RGB+depth / depth with v_depths given (channels = %d)", channels);
+    UBS_CHECK_ARG(v_depths == nullptr || (splat_colors && (channels == 4 || channels == 1)),
+                  "rasterize_bwd: v_depths goes with splat colours of 4 or 1 channels");
     cudaStream_t s = (cudaStream_t)stream;
 #define UBS_BWD_CASE(CH)                                                                                               \
     case CH:                                                                                                           \
         return launch_bwd<CH>(C, N, n_isects, isect_capacity, means2d, conics, colors, opacities, betas, backgrounds,  \
                               masks, width, height, offsets, flatten_ids, render_alphas, last_ids, v_render_colors,    \
-                              v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas, splats, splat_colors, s);
+                              v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas, splats, splat_colors,      \
+                              v_depths, s);
     switch (channels) {
         UBS_BWD_CASE(1)
         UBS_BWD_CASE(2)
@@ -585,7 +603,7 @@ extern "C" int ubs_rasterize_bwd(int C, int64_t N, const int64_t *n_isects, int6
     return rasterize_bwd_impl(C, N, n_isects, isect_capacity, means2d, conics, colors, opacities, betas, backgrounds, masks,
                               channels, width, height, tile_size, offsets, flatten_ids, render_alphas, last_ids,
                               v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas,
-                              nullptr, 0, stream);
+                              nullptr, 0, nullptr, stream);
 }
 
 extern "C" int ubs_rasterize_bwd_splats(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
@@ -595,11 +613,11 @@ extern "C" int ubs_rasterize_bwd_splats(int C, int64_t N, const int64_t *n_isect
                                         const float *render_alphas, const int32_t *last_ids,
                                         const float *v_render_colors, const float *v_render_alphas, float *v_means2d,
                                         float *v_conics, float *v_colors, float *v_opacities, float *v_betas,
-                                        void *stream) {
+                                        float *v_depths, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(splats != nullptr || N == 0 || C == 0 || isect_capacity == 0, "rasterize_bwd_splats: splats is null");
     return rasterize_bwd_impl(C, N, n_isects, isect_capacity, nullptr, nullptr, colors, nullptr, nullptr, backgrounds, masks,
                               channels, width, height, tile_size, offsets, flatten_ids, render_alphas, last_ids,
                               v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas,
-                              splats, colors == nullptr ? 1 : 0, stream);
+                              splats, colors == nullptr ? 1 : 0, colors == nullptr ? v_depths : nullptr, stream);
 }

@@ -102,11 +102,18 @@ rasterize_fwd_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev,
                 const float4 *sp = splats + (size_t)g * 3;
                 r_xyob = sp[0];
                 r_conic = sp[1];
-                if (CH == 3 && splat_colors) {
-                    const float4 c4 = sp[2];
-                    r_color[0] = c4.x;
-                    if constexpr (CH > 1) r_color[1] = c4.y;
-                    if constexpr (CH > 2) r_color[2] = c4.z;
+                if ((CH == 1 || CH == 3 || CH == 4) && splat_colors) {
+                    // colours out of the row itself: RGB (CH = 3), RGB + depth (CH = 4, render modes "RGB+D" / "RGB+ED"),
+                    // depth alone (CH = 1, "Depth" / "EDepth" / "Normal") -- reference: rendering.py:131-142
+                    if constexpr (CH == 1) {
+                        r_color[0] = r_conic.w;
+                    } else {
+                        const float4 c4 = sp[2];
+                        r_color[0] = c4.x;
+                        if constexpr (CH > 1) r_color[1] = c4.y;
+                        if constexpr (CH > 2) r_color[2] = c4.z;
+                        if constexpr (CH > 3) r_color[3] = c4.w;
+                    }
                 } else {
 #pragma unroll
                     for (int k = 0; k < CH; ++k) r_color[k] = colors[(size_t)g * CH + k];
@@ -354,7 +361,8 @@ static int rasterize_fwd_impl(int C, int64_t N, const int64_t *n_isects, int64_t
                   "rasterize_fwd: null primitive arrays");
     UBS_CHECK_ARG(C <= 65535, "rasterize_fwd: C=%d exceeds 65535", C);
     UBS_CHECK_ARG(((uintptr_t)splats & 15) == 0, "rasterize_fwd: splats must be 16-byte aligned");
-    UBS_CHECK_ARG(!splat_colors || channels == 3, "rasterize_fwd: splat colours are RGB (channels = %d)", channels);
+    UBS_CHECK_ARG(!splat_colors || channels == 3 || channels == 4 || channels == 1,
+                  "rasterize_fwd: splat colours are RGB, RGB+depth or depth (channels = %d)", channels);
     cudaStream_t s = (cudaStream_t)stream;
 #define UBS_FWD_CASE(CH)                                                                                               \
     case CH:                                                                                                           \

@@ -6,13 +6,14 @@ activations + covariance build + conditioning + projection + tile count for all 
 capacity-bounded so its length never has to visit the host, and all scratch is allocated once and reused.
 """
 import math
+import warnings
 from typing import Optional
 
 import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import check, ptr
+from ._lib import UbsError, check, ptr
 
 
 def record_stride(D: int) -> int:
@@ -69,14 +70,23 @@ class _StageTimer:
 class FusedRasterizer:
     """Persistent buffers + the launch sequence fused-project -> emit/sort/offsets -> composite.
 
-    `capacity` bounds the number of (primitive, tile) pairs.  It grows automatically: the pair count of every
-    frame is copied to pinned host memory asynchronously and inspected (without blocking) on the next call.
-    `overflowed()` tells whether the most recent completed frame was truncated.
+    `capacity` bounds the number of (primitive, tile) pairs (default 8 C N; a 3M-primitive 1080p frame has ~2 N).
+    A frame that exceeds it is TRUNCATED on the device, and that is never silent:
+      * the device word `status[0]` says whether the most recent frame was truncated, `status[1]` counts truncated
+        frames; every projection-backward entry point takes `status` as its skip flag, so a truncated frame contributes
+        no gradient and the fused Adam update of such a frame is not applied at all;
+      * pair count and status of every frame are copied to pinned host memory asynchronously and inspected (without
+        blocking) by the following calls: the buffers grow BEFORE they overflow (at 85 % fill) and, if a frame was
+        truncated all the same, `on_overflow` decides: "warn" (default) emits a RuntimeWarning, "raise" raises
+        UbsError from the next forward(); `truncated_frames` counts them;
+      * the autograd wrapper `render()` additionally refuses to differentiate a frame it knows to be truncated.
+    `frame_id` numbers the forward() calls; backward() works on the most recent frame only and the autograd wrapper
+    raises when asked to differentiate a stale one.
     """
 
     def __init__(self, D: int, N: int, width: int, height: int, n_cams: int = 1, capacity: Optional[int] = None,
                  tile_size: int = 16, device="cuda", eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0,
-                 antialiased=False, sort_mode: str = "bin"):
+                 antialiased=False, sort_mode: str = "bin", on_overflow: str = "warn"):
         self.lib = _lib.load()
         self.D, self.N, self.W, self.H, self.C = D, N, width, height, n_cams
         self.tile_size = tile_size
@@ -101,13 +111,20 @@ class FusedRasterizer:
         self.splats = torch.empty((C, N, 12), dtype=f32, device=dev)
         self.tiles_per_gauss = torch.empty((C, N), dtype=i32, device=dev)
         self.n_isects = torch.zeros((1,), dtype=torch.int64, device=dev)
-        self.status = torch.zeros((1,), dtype=i32, device=dev)
+        self.status = torch.zeros((2,), dtype=i32, device=dev)  # [truncated now, truncated frames so far]
+        assert on_overflow in ("warn", "raise")
+        self.on_overflow = on_overflow
+        self.frame_id = 0          # number of forward() calls so far; the frame backward() differentiates
+        self.truncated_frames = 0  # as seen by the host (lags the device by a frame or two)
+        self.channels = 3          # colour channels of the most recent frame (3 RGB, 4 RGB+depth, 1 depth)
+        self._extra_out = {}
         self.offsets = torch.empty((C, self.th, self.tw), dtype=i32, device=dev)
         self.render_colors = torch.empty((C, height, width, 3), dtype=f32, device=dev)
         self.render_alphas = torch.empty((C, height, width, 1), dtype=f32, device=dev)
         self.last_ids = torch.empty((C, height, width), dtype=i32, device=dev)
         self._host_count = torch.zeros((2,), dtype=torch.int64).pin_memory()
-        self._count_event = None
+        self._host_status = torch.zeros((2,), dtype=torch.int32).pin_memory()
+        self._count_event, self._count_frame = None, 0
         self._alloc_pairs(capacity if capacity is not None else max(8 * C * N, 1 << 16))
         self.stage_events = None  # dict stage -> [(start, end)] when enable_stage_timing() was called
 
@@ -147,37 +164,70 @@ class FusedRasterizer:
             nbytes = self.lib.ubs_isect_workspace_bytes(self.C * self.N, self.capacity)
         self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
 
-    def _poll_count(self):
-        """Non-blocking look at the previous frame's pair count; grows the pair buffers when needed."""
-        if self._count_event is not None and self._count_event.query():
-            n = int(self._host_count[0])
-            self._count_event = None
-            if n > self.capacity:
-                self._alloc_pairs(int(n * 1.25) + 1024)
-                self.status.zero_()
+    def _poll_count(self, block: bool = False):
+        """Look at the pair count / truncation status an earlier frame left in pinned memory (non-blocking unless
+        `block`); grows the pair buffers ahead of need and reports truncated frames (class docstring)."""
+        if self._count_event is None:
+            return
+        if block:
+            self._count_event.synchronize()
+        elif not self._count_event.query():
+            return
+        n, n_trunc = int(self._host_count[0]), int(self._host_status[1])
+        self._count_event = None
+        if n > 0.85 * self.capacity:
+            self._alloc_pairs(int(n * 1.5) + 1024)
+        if n_trunc > self.truncated_frames:
+            new = n_trunc - self.truncated_frames
+            self.truncated_frames = n_trunc
+            msg = ("%d frame(s) exceeded the pair capacity and were truncated (last pair count %d); their gradients "
+                   "were dropped and the buffers have been grown to %d pairs" % (new, n, self.capacity))
+            if self.on_overflow == "raise":
+                raise UbsError(msg)
+            warnings.warn(msg, RuntimeWarning, stacklevel=3)
 
     def last_pair_count(self) -> int:
         """Blocking read of the last frame's pair count (diagnostics / tests)."""
         return int(self.n_isects.item())
 
     def overflowed(self) -> bool:
-        return bool(self.status.item() & 1)
+        """Was the most recent frame truncated?  (Blocking read of the device status word.)"""
+        return bool(self.status[0].item())
+
+    def _color_buffer(self, channels: int) -> Tensor:
+        if channels == 3:
+            return self.render_colors
+        buf = self._extra_out.get(channels)
+        if buf is None:
+            buf = torch.empty((self.C, self.H, self.W, channels), dtype=torch.float32, device=self.device)
+            self._extra_out[channels] = buf
+        return buf
 
     @torch.no_grad()
     def forward(self, records: Tensor, viewmats: Tensor, Ks: Tensor, cam_pos: Tensor,
                 timestamps: Optional[Tensor] = None, backgrounds: Optional[Tensor] = None,
-                prim_mask: Optional[Tensor] = None, out=None):
+                prim_mask: Optional[Tensor] = None, out=None, channels: int = 3, activated: bool = False,
+                query: Optional[Tensor] = None):
         """records [N,stride], viewmats [C,4,4], Ks [C,3,3], cam_pos [C,3], timestamps [C] (D=7),
-        backgrounds [C,3] -> (render_colors [C,H,W,3], render_alphas [C,H,W,1]).  The images land in buffers owned
-        by self, or in `out` = (colors, alphas) when given (backward() needs the default buffers)."""
+        backgrounds [C,channels] -> (render_colors [C,H,W,channels], render_alphas [C,H,W,1]).  The images land in
+        buffers owned by self, or in `out` = (colors, alphas) when given (backward() needs the default alphas).
+        channels: 3 = RGB; 4 = RGB + depth ("RGB+D" / "RGB+ED"); 1 = depth ("Depth" / "EDepth" / "Normal") --
+        submodules/gsplat/rendering.py:131-142; the depth channel comes out of the same 48-byte splat rows.
+        activated / query: see ubs_fused_project_fwd (the drop-in route)."""
         lib, s = self.lib, torch.cuda.current_stream().cuda_stream
         C, N, D = self.C, self.N, self.D
         assert records.shape == (N, record_stride(D)) and records.is_cuda and records.dtype == torch.float32
         assert records.is_contiguous()
-        assert viewmats.shape == (C, 4, 4) and Ks.shape == (C, 3, 3) and cam_pos.shape == (C, 3)
+        assert viewmats.shape == (C, 4, 4) and Ks.shape == (C, 3, 3)
+        assert query is not None or cam_pos.shape == (C, 3)
+        assert query is None or (query.shape == (N, D - 3) and query.is_contiguous() and query.dtype == torch.float32)
+        assert channels in (1, 3, 4)
+        assert backgrounds is None or (backgrounds.shape == (C, channels) and backgrounds.is_contiguous())
         self._poll_count()
-        rc_out, ra_out = (self.render_colors, self.render_alphas) if out is None else out
-        assert rc_out.shape == self.render_colors.shape and ra_out.shape == self.render_alphas.shape
+        self.frame_id += 1
+        self.channels = channels
+        rc_out, ra_out = (self._color_buffer(channels), self.render_alphas) if out is None else out
+        assert rc_out.shape == (C, self.H, self.W, channels) and ra_out.shape == self.render_alphas.shape
         assert rc_out.is_contiguous() and ra_out.is_contiguous() and rc_out.dtype == torch.float32
         mask_u8 = None if prim_mask is None else prim_mask.to(torch.bool).contiguous().view(torch.uint8)
         with self._stage("fused_project_fwd"):
@@ -187,7 +237,7 @@ class FusedRasterizer:
             ptr(self.radii), ptr(self.means2d), ptr(self.depths), ptr(self.conics), ptr(self.opacities),
             ptr(self.betas), ptr(self.colors), ptr(self.tiles_per_gauss), ptr(self.splats),
             ptr(self.workspace) if self.sort_mode == "bin" else None, ptr(self.n_isects), ptr(self.workspace),
-            self.workspace.numel(), s), "ubs_fused_project_fwd")
+            self.workspace.numel(), 1 if activated else 0, ptr(query), s), "ubs_fused_project_fwd")
         with self._stage("isect_emit_sort_offsets"):
           if self.sort_mode == "bin":
             check(lib.ubs_isect_bin_sort(
@@ -202,87 +252,103 @@ class FusedRasterizer:
               self.workspace.numel(), s), "ubs_isect_emit_sort")
         with self._stage("rasterize_fwd"):
           check(lib.ubs_rasterize_fwd_splats(
-            C, N, ptr(self.n_isects), self.capacity, ptr(self.splats), None, ptr(backgrounds), None, 3, self.W, self.H,
-            self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(rc_out), ptr(ra_out), ptr(self.last_ids), s),
-            "ubs_rasterize_fwd_splats")
+            C, N, ptr(self.n_isects), self.capacity, ptr(self.splats), None, ptr(backgrounds), None, channels, self.W,
+            self.H, self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(rc_out), ptr(ra_out),
+            ptr(self.last_ids), s), "ubs_rasterize_fwd_splats")
         if self._count_event is None:
             self._host_count[0:1].copy_(self.n_isects, non_blocking=True)
+            self._host_status.copy_(self.status, non_blocking=True)
             self._count_event = torch.cuda.Event()
             self._count_event.record()
+            self._count_frame = self.frame_id
         return rc_out, ra_out
 
     def _grad_buffers(self):
         if getattr(self, "_gflat", None) is None:
             C, N = self.C, self.N
-            self._gflat = torch.empty((C * N * 10,), dtype=torch.float32, device=self.device)
+            self._gflat = torch.empty((C * N * 11,), dtype=torch.float32, device=self.device)
             o = 0
             views = []
-            for w, shape in ((2, (C, N, 2)), (3, (C, N, 3)), (3, (C, N, 3)), (1, (C, N)), (1, (C, N))):
+            for w, shape in ((2, (C, N, 2)), (3, (C, N, 3)), (3, (C, N, 3)), (1, (C, N)), (1, (C, N)), (1, (C, N))):
                 views.append(self._gflat[o:o + C * N * w].view(shape))
                 o += C * N * w
-            self.v_means2d, self.v_conics, self.v_colors, self.v_opacities, self.v_betas = views
-        return self._gflat
+            self.v_means2d, self.v_conics, self.v_colors, self.v_opacities, self.v_betas, self.v_depths = views
+        # the depth gradients (last C N floats) are only produced by the 4- and 1-channel modes
+        return self._gflat if self.channels != 3 else self._gflat[:self.C * self.N * 10]
 
     @torch.no_grad()
     def backward(self, records: Tensor, viewmats: Tensor, Ks: Tensor, cam_pos: Tensor, timestamps: Optional[Tensor],
                  backgrounds: Optional[Tensor], v_render_colors: Tensor, v_render_alphas: Tensor,
                  v_records: Optional[Tensor] = None, adam=None, opacity_reg: float = 0.0,
-                 scale_reg: float = 0.0) -> Optional[Tensor]:
+                 scale_reg: float = 0.0, activated: bool = False, query: Optional[Tensor] = None,
+                 alphas: Optional[Tensor] = None) -> Optional[Tensor]:
         """Gradient of the most recent forward() w.r.t. the packed records ([N, stride], same layout).
         Must be called before the next forward(): it reuses that frame's tile lists and screen-space records.
         With `adam` (a training.PackedAdam) the optimiser step is applied inside the projection-backward kernel:
         `records` and the moments are updated in place, no gradient buffer is produced and None is returned."""
         lib, s = self.lib, torch.cuda.current_stream().cuda_stream
         C, N, D = self.C, self.N, self.D
-        self.composite_backward(backgrounds, v_render_colors, v_render_alphas)
+        self.composite_backward(backgrounds, v_render_colors, v_render_alphas, alphas)
         if adam is not None:
             # single-GPU batch-1 training: projection backward + Adam in one launch, records updated in place
             import ctypes
 
+            assert not activated and query is None, "the fused Adam update works on raw parameter records"
             adam.step_count += 1
             cols = (ctypes.c_double * adam.stride)(*adam.lr_columns())
             with self._stage("fused_project_bwd_adam"):
               check(lib.ubs_fused_project_bwd_adam(
                 C, N, D, ptr(records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), self.W, self.H,
-                self.eps2d, 1 if self.aa else 0, ptr(self.radii), ptr(self.conics), ptr(self.v_means2d), None,
+                self.eps2d, 1 if self.aa else 0, ptr(self.radii), ptr(self.conics), ptr(self.v_means2d),
+                ptr(self.v_depths) if self.channels != 3 else None,
                 ptr(self.v_conics), ptr(self.v_opacities), ptr(self.v_betas), ptr(self.v_colors), ptr(adam.exp_avg),
                 ptr(adam.exp_avg_sq), ctypes.cast(cols, ctypes.c_void_p), adam.betas[0], adam.betas[1], adam.eps,
-                adam.step_count, float(opacity_reg), float(scale_reg), s), "ubs_fused_project_bwd_adam")
+                adam.step_count, float(opacity_reg), float(scale_reg), ptr(self.status), s),
+                "ubs_fused_project_bwd_adam")
             return None
         if v_records is None:
             v_records = torch.empty_like(records)
         with self._stage("fused_project_bwd"):
-            self.project_backward_rows(records, viewmats, Ks, cam_pos, timestamps, v_records, 0, N)
+            self.project_backward_rows(records, viewmats, Ks, cam_pos, timestamps, v_records, 0, N, activated, query)
         return v_records
 
     @torch.no_grad()
-    def composite_backward(self, backgrounds: Optional[Tensor], v_render_colors: Tensor, v_render_alphas: Tensor):
-        """First half of backward(): screen-space gradients of the most recent forward() into self.v_*."""
+    def composite_backward(self, backgrounds: Optional[Tensor], v_render_colors: Tensor, v_render_alphas: Tensor,
+                           alphas: Optional[Tensor] = None):
+        """First half of backward(): screen-space gradients of the most recent forward() into self.v_*.
+        alphas: the frame's alpha image when forward() wrote it to `out` instead of self.render_alphas."""
+        alphas = self.render_alphas if alphas is None else alphas
+        assert alphas.shape == self.render_alphas.shape and alphas.is_contiguous()
         lib, s = self.lib, torch.cuda.current_stream().cuda_stream
         C, N = self.C, self.N
-        self._grad_buffers().zero_()  # one memset for all five screen-space gradient arrays
-        v_rc, v_ra = v_render_colors.contiguous(), v_render_alphas.contiguous()
-        assert v_rc.shape == (C, self.H, self.W, 3) and v_ra.shape == (C, self.H, self.W, 1)
+        ch = self.channels
+        self._grad_buffers().zero_()  # one memset for all the screen-space gradient arrays
+        v_rc, v_ra = v_render_colors.contiguous(), v_render_alphas.contiguous()  # locals: alive until after the launch
+        assert v_rc.shape == (C, self.H, self.W, ch) and v_ra.shape == (C, self.H, self.W, 1)
         with self._stage("rasterize_bwd"):
           check(lib.ubs_rasterize_bwd_splats(
-            C, N, ptr(self.n_isects), self.capacity, ptr(self.splats), None, ptr(backgrounds), None, 3, self.W, self.H,
-            self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(self.render_alphas), ptr(self.last_ids),
+            C, N, ptr(self.n_isects), self.capacity, ptr(self.splats), None, ptr(backgrounds), None, ch, self.W, self.H,
+            self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(alphas), ptr(self.last_ids),
             ptr(v_rc), ptr(v_ra), ptr(self.v_means2d), ptr(self.v_conics), ptr(self.v_colors), ptr(self.v_opacities),
-            ptr(self.v_betas), s), "ubs_rasterize_bwd_splats")
+            ptr(self.v_betas), ptr(self.v_depths) if ch != 3 else None, s), "ubs_rasterize_bwd_splats")
 
     @torch.no_grad()
-    def project_backward_rows(self, records, viewmats, Ks, cam_pos, timestamps, v_records, begin: int, count: int):
+    def project_backward_rows(self, records, viewmats, Ks, cam_pos, timestamps, v_records, begin: int, count: int,
+                              activated: bool = False, query: Optional[Tensor] = None):
         """Second half of backward() for primitives [begin, begin + count): gradient records of those rows from
         self.v_*.  Row ranges are independent, so a caller can pipeline them against a collective (one camera)."""
         assert self.C == 1 or (begin == 0 and count == self.N), "row ranges need the [C, N] arrays to be [1, N]"
         if count == 0:
             return
         sl = slice(begin, begin + count)
+        # row slices of the [1, N, ...] arrays are views at an offset: no temporaries whose address could be recycled
         check(self.lib.ubs_fused_project_bwd(
             self.C, count, self.D, ptr(records[sl]), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), self.W,
             self.H, self.eps2d, 1 if self.aa else 0, ptr(self.radii[:, sl]), ptr(self.conics[:, sl]),
-            ptr(self.v_means2d[:, sl]), None, ptr(self.v_conics[:, sl]), ptr(self.v_opacities[:, sl]),
-            ptr(self.v_betas[:, sl]), ptr(self.v_colors[:, sl]), ptr(v_records[sl]),
+            ptr(self.v_means2d[:, sl]), ptr(self.v_depths[:, sl]) if self.channels != 3 else None,
+            ptr(self.v_conics[:, sl]), ptr(self.v_opacities[:, sl]),
+            ptr(self.v_betas[:, sl]), ptr(self.v_colors[:, sl]), ptr(v_records[sl]), 1 if activated else 0,
+            ptr(None if query is None else query[sl]), ptr(self.status),
             torch.cuda.current_stream().cuda_stream), "ubs_fused_project_bwd")
 
 
@@ -349,26 +415,47 @@ class _FusedRender(torch.autograd.Function):
     """records -> (render_colors, render_alphas) with gradients to the packed records and the backgrounds."""
 
     @staticmethod
-    def forward(ctx, records, rz, viewmats, Ks, cam_pos, timestamps, backgrounds):
-        rc, ra = rz.forward(records, viewmats, Ks, cam_pos, timestamps, backgrounds)
-        ctx.rz = rz
-        ctx.save_for_backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds)
+    def forward(ctx, records, rz, viewmats, Ks, cam_pos, timestamps, backgrounds, channels, activated, query):
+        C, H, W = rz.C, rz.H, rz.W
+        # fresh output tensors: autograd nodes downstream (the loss) save the image, and the rasteriser's own
+        # buffers are overwritten by its next frame
+        out = (torch.empty((C, H, W, channels), dtype=torch.float32, device=rz.device),
+               torch.empty((C, H, W, 1), dtype=torch.float32, device=rz.device))
+        rc, ra = rz.forward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, out=out, channels=channels,
+                            activated=activated, query=query)
+        ctx.rz, ctx.frame_id, ctx.activated = rz, rz.frame_id, activated
+        ctx.save_for_backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, query, ra)
         return rc, ra
 
     @staticmethod
     def backward(ctx, v_rc, v_ra):
-        records, viewmats, Ks, cam_pos, timestamps, backgrounds = ctx.saved_tensors
+        records, viewmats, Ks, cam_pos, timestamps, backgrounds, query, ra = ctx.saved_tensors
         rz = ctx.rz
-        v_records = rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, v_rc, v_ra)
+        if rz.frame_id != ctx.frame_id:
+            raise UbsError(
+                "stale frame: this FusedRasterizer has rendered %d frame(s) since the one being differentiated; its tile "
+                "lists and screen-space records are gone.  Call backward() before the next render on the same "
+                "rasteriser, or give every frame in flight its own FusedRasterizer (ubs_b200.dropin keeps a pool)"
+                % (rz.frame_id - ctx.frame_id))
+        # the frame's pair count has normally reached the host by now: refuse to differentiate a truncated frame
+        # (without blocking; if the copy is still in flight the device-side skip flag zeroes the gradient instead)
+        if (rz._count_event is not None and rz._count_frame == ctx.frame_id and rz._count_event.query()
+                and int(rz._host_status[0]) != 0):
+            rz._poll_count()
+            raise UbsError("the frame being differentiated was truncated (pair capacity exceeded); render it again -- "
+                           "the buffers have been grown to %d pairs" % rz.capacity)
+        v_records = rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, v_rc, v_ra,
+                                activated=ctx.activated, query=query, alphas=ra)
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[6]:
-            v_bg = (v_rc * (1.0 - rz.render_alphas)).sum(dim=(1, 2))
-        return v_records, None, None, None, None, None, v_bg
+            v_bg = (v_rc * (1.0 - ra)).sum(dim=(1, 2))
+        return v_records, None, None, None, None, None, v_bg, None, None, None
 
 
 def render(records: Tensor, rz: FusedRasterizer, viewmats: Tensor, Ks: Tensor, cam_pos: Tensor,
-           timestamps: Optional[Tensor] = None, backgrounds: Optional[Tensor] = None):
+           timestamps: Optional[Tensor] = None, backgrounds: Optional[Tensor] = None, channels: int = 3,
+           activated: bool = False, query: Optional[Tensor] = None):
     """Differentiable fused render: the equivalent of BetaModel.render (scene/beta_model.py:660-722) for C cameras
-    at once.  Returns (render_colors [C,H,W,3], render_alphas [C,H,W,1]); the buffers belong to `rz` and are
-    overwritten by its next forward()."""
-    return _FusedRender.apply(records, rz, viewmats, Ks, cam_pos, timestamps, backgrounds)
+    at once.  Returns freshly allocated (render_colors [C,H,W,channels], render_alphas [C,H,W,1]).  backward() must
+    run before `rz` renders its next frame (it raises otherwise)."""
+    return _FusedRender.apply(records, rz, viewmats, Ks, cam_pos, timestamps, backgrounds, channels, activated, query)

@@ -4,11 +4,12 @@
   * PackedBetaModel.view(c2w, K, W, H, ...)              <->  BetaModel.view        (scene/beta_model.py:724-831)
   * quantile_mask                                        <->  the viewer's beta-quantile primitive filter (:729-755)
 
-"RGB" (and the viewer's "Alpha") go through the fused fast path (fused.FusedRasterizer; the primitive mask is
-applied inside the projection kernel, no gather of the parameters); the depth / normal modes, which need depth as
-a colour channel, go through the reference-shaped operator chain (ops.* + rendering.rasterization).  The colour
-mapping of depth images (utils/general_utils.py:196-220, matplotlib's "turbo") is presentation and stays with the
-viewer.
+Every render mode goes through the fused fast path (fused.FusedRasterizer; the primitive mask is applied inside the
+projection kernel, no gather of the parameters): "RGB" / the viewer's "Alpha" composite the RGB of the 48-byte splat
+rows, "RGB+D" / "RGB+ED" its RGB + depth, "Depth" / "EDepth" / "Normal" its depth alone
+(submodules/gsplat/rendering.py:131-142,219-230).  `chain=True` forces the reference-shaped operator chain
+(ops.* + rendering.rasterization) instead -- what the parity tests compare the fused modes with.  The colour mapping
+of depth images (utils/general_utils.py:196-220, matplotlib's "turbo") is presentation and stays with the viewer.
 """
 from typing import Dict, Optional, Sequence
 
@@ -16,7 +17,9 @@ import torch
 from torch import Tensor
 
 from . import fused, ops
-from .rendering import rasterization
+from .rendering import _finish, rasterization
+
+_CHANNELS = {"RGB": 3, "Alpha": 3, "RGB+D": 4, "RGB+ED": 4, "Depth": 1, "EDepth": 1, "Normal": 1}
 
 
 def quantile_mask(beta_raw: Tensor, b_xyz=(0, 100), b_view=(0, 100), b_time: Optional[Sequence[float]] = (0, 100)):
@@ -85,14 +88,19 @@ class PackedBetaModel:
         return means, covs, opac.squeeze(-1), b[:, 0].contiguous(), rgb
 
     @torch.no_grad()
-    def _render(self, viewmat, K, cam_pos, timestamp, W, H, render_mode, mask, near, far, clip):
+    def _render(self, viewmat, K, cam_pos, timestamp, W, H, render_mode, mask, near, far, clip, chain=False):
         dev = self.records.device
         bg = self.background.reshape(1, 3).to(dev)
-        if render_mode in ("RGB", "Alpha"):
+        if not chain:
+            ch = _CHANNELS[render_mode]
             rz = self._rasterizer(W, H, near, far, clip)
             ts = torch.tensor([float(timestamp)], device=dev) if self.D == 7 else None
-            rc, ra = rz.forward(self.records, viewmat[None].contiguous(), K[None].contiguous(),
-                                cam_pos[None].contiguous(), ts, bg, prim_mask=mask)
+            # depth channel / depth-only images composite over a zero background (rendering.py:131-142)
+            bg_ch = bg if ch == 3 else (torch.cat([bg, bg.new_zeros(1, 1)], dim=-1) if ch == 4 else bg.new_zeros(1, 1))
+            vm, Kc = viewmat[None].contiguous(), K[None].contiguous()
+            rc, ra = rz.forward(self.records, vm, Kc, cam_pos[None].contiguous(), ts, bg_ch.contiguous(),
+                                prim_mask=mask, channels=ch)
+            rc = _finish(rc, ra, "RGB" if render_mode == "Alpha" else render_mode, vm, Kc)
             meta = {"means2d": rz.means2d, "radii": rz.radii}
             return rc, ra, meta
         means, covs, opac, beta0, rgb = self._conditioned(cam_pos, timestamp)
@@ -100,22 +108,22 @@ class PackedBetaModel:
             mask = torch.ones(self.N, dtype=torch.bool, device=dev)
         return rasterization(means[mask], None, None, opac[mask], beta0[mask], rgb[mask], viewmat[None], K[None], W, H,
                              near_plane=near, far_plane=far, radius_clip=clip, backgrounds=bg,
-                             render_mode=render_mode, covars=covs[mask])
+                             render_mode="RGB" if render_mode == "Alpha" else render_mode, covars=covs[mask])
 
-    def render(self, camera, render_mode: str = "RGB", mask: Optional[Tensor] = None):
+    def render(self, camera, render_mode: str = "RGB", mask: Optional[Tensor] = None, chain: bool = False):
         """camera: anything with viewmat [4,4] (world->camera, row-major), K [3,3], cam_pos [3], width, height,
         timestamp (synth.Camera).  Returns the reference's dict (scene/beta_model.py:716-722); with a mask, the
         fused path keeps the per-primitive outputs at full length N (masked-out primitives have radius 0), the
         operator chain returns them for the kept primitives only, like the reference."""
         rc, ra, meta = self._render(camera.viewmat, camera.K, camera.cam_pos, camera.timestamp, camera.width,
-                                    camera.height, render_mode, mask, 0.01, 1e10, 0.0)
+                                    camera.height, render_mode, mask, 0.01, 1e10, 0.0, chain)
         return {"render": rc.permute(0, 3, 1, 2).contiguous()[0], "alpha": ra, "viewspace_points": meta["means2d"],
                 "visibility_filter": meta["radii"] > 0, "radii": meta["radii"], "is_used": meta["radii"] > 0}
 
     @torch.no_grad()
     def view(self, c2w: Tensor, K: Tensor, W: int, H: int, render_mode: str = "RGB", b_xyz=(0, 100), b_view=(0, 100),
              b_time=(0, 100), timestamp: float = 0.0, near_plane: float = 0.01, far_plane: float = 1e10,
-             radius_clip: float = 0.0, backgrounds=(0, 0, 0)):
+             radius_clip: float = 0.0, backgrounds=(0, 0, 0), chain: bool = False):
         """The viewer callback (scene/beta_model.py:724-831) without the GUI state object: returns
         (image [H,W,ch] on the device, rendered primitive count).  Depth modes return the raw 1-channel image."""
         dev = self.records.device
@@ -125,7 +133,7 @@ class PackedBetaModel:
         self.background = torch.tensor(backgrounds, device=dev, dtype=torch.float32) / 255.0
         viewmat = torch.linalg.inv(c2w)
         rc, ra, meta = self._render(viewmat, K, c2w[:3, 3].contiguous(), timestamp, W, H,
-                                    render_mode, mask, near_plane, far_plane, radius_clip)
+                                    render_mode, mask, near_plane, far_plane, radius_clip, chain)
         if render_mode == "Alpha":
             rc = ra
         return rc[0], int((meta["radii"] > 0).sum().item())

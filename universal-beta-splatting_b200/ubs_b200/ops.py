@@ -58,11 +58,12 @@ def projection_bwd(means, covars, viewmats, Ks, width, height, eps2d, radii, con
     v_means = torch.empty((N, 3), dtype=torch.float32, device=dev)
     v_covars = torch.empty((N, 6), dtype=torch.float32, device=dev)
     v_viewmats = torch.empty((C, 4, 4), dtype=torch.float32, device=dev) if viewmats_requires_grad else None
+    # contiguous copies are bound to locals so that they outlive the launch (upstream gradients are often views)
+    v_means2d, v_depths, v_conics = _req(v_means2d, "v_means2d"), _req(v_depths, "v_depths"), _req(v_conics, "v_conics")
+    v_comp = None if v_compensations is None else _req(v_compensations, "v_compensations")
     check(lib.ubs_projection_bwd(C, N, ptr(means), ptr(covars), ptr(viewmats), ptr(Ks), int(width), int(height),
                                  float(eps2d), ptr(radii), ptr(conics), ptr(compensations),
-                                 ptr(_req(v_means2d, "v_means2d")), ptr(_req(v_depths, "v_depths")),
-                                 ptr(_req(v_conics, "v_conics")),
-                                 ptr(None if v_compensations is None else _req(v_compensations, "v_compensations")),
+                                 ptr(v_means2d), ptr(v_depths), ptr(v_conics), ptr(v_comp),
                                  ptr(v_means), ptr(v_covars), ptr(v_viewmats), _stream()),
           "ubs_projection_bwd")
     return v_means, v_covars, v_viewmats
@@ -266,11 +267,11 @@ def rasterize_bwd(means2d, conics, colors, opacities, betas, backgrounds, masks,
     v_colors = torch.zeros_like(colors)
     v_opacities = torch.zeros_like(opacities)
     v_betas = torch.zeros_like(betas)
+    v_rc, v_ra = _req(v_render_colors, "v_render_colors"), _req(v_render_alphas, "v_render_alphas")  # outlive the launch
     check(lib.ubs_rasterize_bwd(C, N, ptr(n_isects_dev), flatten_ids.numel(), ptr(means2d), ptr(conics), ptr(colors), ptr(opacities),
                                 ptr(betas), ptr(backgrounds), ptr(masks), ch, int(width), int(height), int(tile_size),
                                 ptr(isect_offsets), ptr(flatten_ids), ptr(render_alphas), ptr(last_ids),
-                                ptr(_req(v_render_colors, "v_render_colors")),
-                                ptr(_req(v_render_alphas, "v_render_alphas")), ptr(v_means2d), ptr(v_conics),
+                                ptr(v_rc), ptr(v_ra), ptr(v_means2d), ptr(v_conics),
                                 ptr(v_colors), ptr(v_opacities), ptr(v_betas), _stream()),
           "ubs_rasterize_bwd")
     return v_means2d, v_conics, v_colors, v_opacities, v_betas
@@ -411,8 +412,6 @@ def _check_rest_layout(D: int, rest_i: Tensor, rest_j: Tensor):
         raise NotImplementedError("rest_i/rest_j must be the tril_indices layout built by scene/beta_model.py:69-73")
 
 
-_REST_OK = set()
-
 
 class _RotScaleLTriangleToCovar(torch.autograd.Function):
     """Mirror of cuda/_wrapper.py:633-684."""
@@ -438,8 +437,9 @@ class _RotScaleLTriangleToCovar(torch.autograd.Function):
         lib = _lib.load()
         N, D = scale.shape
         v_rot, v_scale, v_lt = torch.empty_like(rot), torch.empty_like(scale), torch.empty_like(l_triangle)
+        v_covar = _req(v_covar, "v_covar")
         check(lib.ubs_rot_scale_l_triangle_to_covar_bwd(N, D, 1 if ctx.spatial else 0, ptr(rot), ptr(scale),
-                                                        ptr(l_triangle), ptr(_req(v_covar, "v_covar")), ptr(v_rot),
+                                                        ptr(l_triangle), ptr(v_covar), ptr(v_rot),
                                                         ptr(v_scale), ptr(v_lt), _stream()),
               "ubs_rot_scale_l_triangle_to_covar_bwd")
         return v_rot, v_scale, v_lt, None
@@ -449,10 +449,12 @@ def rot_scale_l_triangle_to_covar(rot: Tensor, scale: Tensor, l_triangle: Tensor
                                   spatial_block: bool = False) -> Tensor:
     """Sigma = L L^T (cuda/_wrapper.py:39-55).  D in [4, 8]."""
     D = scale.shape[1]
-    key = (D, rest_i.data_ptr(), rest_j.data_ptr())
-    if key not in _REST_OK:  # validated once per index tensor (needs a host copy)
+    # validated once per index-tensor OBJECT and content version (needs a host copy); the mark lives on the tensors
+    # themselves, so a recycled address can never pass for a validated layout
+    mark_i, mark_j = (D, "i", rest_i._version), (D, "j", rest_j._version)
+    if getattr(rest_i, "_ubs_layout_ok", None) != mark_i or getattr(rest_j, "_ubs_layout_ok", None) != mark_j:
         _check_rest_layout(D, rest_i, rest_j)
-        _REST_OK.add(key)
+        rest_i._ubs_layout_ok, rest_j._ubs_layout_ok = mark_i, mark_j
     assert rot.shape[1:] == (3, 3) and l_triangle.shape[1] == D * (D - 1) // 2
     return _RotScaleLTriangleToCovar.apply(_req(rot, "rot"), _req(scale, "scale"), _req(l_triangle, "l_triangle"),
                                            bool(spatial_block))
@@ -482,9 +484,10 @@ class _CondMeanConvarianceOpacity(torch.autograd.Function):
         N, D = means.shape
         v_means, v_covars = torch.empty_like(means), torch.empty_like(covars)
         v_opac, v_betas = torch.empty_like(opacities), torch.empty_like(betas)
+        v_om, v_oc, v_oo = _req(v_om, "v_means"), _req(v_oc, "v_covars"), _req(v_oo, "v_opacities")  # outlive the launch
         check(lib.ubs_cond_mean_covar_opacity_bwd(N, D, ptr(means), ptr(covars), ptr(opacities), ptr(betas),
-                                                  ptr(query), ptr(_req(v_om, "v_means")), ptr(_req(v_oc, "v_covars")),
-                                                  ptr(_req(v_oo, "v_opacities")), ptr(v_means), ptr(v_covars),
+                                                  ptr(query), ptr(v_om), ptr(v_oc),
+                                                  ptr(v_oo), ptr(v_means), ptr(v_covars),
                                                   ptr(v_opac), ptr(v_betas), _stream()),
               "ubs_cond_mean_covar_opacity_bwd")
         return v_means, v_covars, v_opac, v_betas, None

@@ -47,13 +47,14 @@ def _strides4(t: Tensor, layout: str):
 
 
 class _LossWorkspace:
-    """Per-shape scratch of the loss kernels, cached on the device."""
+    """Per-shape scratch of the loss kernels, cached per device AND stream (two streams computing the loss of the
+    same image shape concurrently must not share scratch)."""
 
     _cache: Dict[tuple, Tensor] = {}
 
     @classmethod
     def get(cls, lib, C, ch, H, W, device) -> Tensor:
-        key = (C, ch, H, W, str(device))
+        key = (C, ch, H, W, str(device), torch.cuda.current_stream(device).cuda_stream)
         ws = cls._cache.get(key)
         if ws is None:
             n = lib.ubs_l1_ssim_workspace_bytes(C, ch, H, W)
@@ -191,9 +192,12 @@ def mcmc_relocate(records: Tensor, D: int, dst_idx: Tensor, src_idx: Tensor, ada
     if K == 0:
         return
     counts = torch.empty((N,), dtype=torch.int32, device=records.device)
+    # bound to locals: a .contiguous() copy must stay alive until after the launch (a temporary's block would be
+    # handed to the next same-sized allocation, and both pointers would name the same memory)
+    dst_c, src_c = dst_idx.contiguous(), src_idx.contiguous()
     check(lib.ubs_mcmc_relocate(N, D, ptr(records), ptr(adam.exp_avg) if adam else None,
-                                ptr(adam.exp_avg_sq) if adam else None, K, ptr(dst_idx.contiguous()),
-                                ptr(src_idx.contiguous()), ptr(counts), torch.cuda.current_stream().cuda_stream),
+                                ptr(adam.exp_avg_sq) if adam else None, K, ptr(dst_c), ptr(src_c), ptr(counts),
+                                torch.cuda.current_stream().cuda_stream),
           "ubs_mcmc_relocate")
 
 
