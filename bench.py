@@ -50,10 +50,11 @@ N_RING = 64
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.004):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.timeline = []  # (perf_counter, sm_mhz, reason bits) for region() queries
         self._stop_evt = threading.Event()
         try:
             import pynvml
@@ -78,17 +79,32 @@ class ClockSampler(threading.Thread):
         }
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                self.samples.append(mhz)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.timeline.append((time.perf_counter(), mhz, r))
+                self.names = names
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
             except Exception:  # pragma: no cover
                 pass
             time.sleep(self.period)
+
+    def region(self, t0, t1):
+        """Clocks line of the samples taken in [t0, t1] (perf_counter)."""
+        sel = [x for x in list(self.timeline) if t0 <= x[0] <= t1]
+        s = sorted(x[1] for x in sel)
+        reasons = set()
+        for _, _, r in sel:
+            for bit, name in getattr(self, "names", {}).items():
+                if r & bit:
+                    reasons.add(name)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                "samples": len(s)}
 
     def stop(self):
         self._stop_evt.set()
@@ -232,6 +248,92 @@ def run_reference_cuda(args, rank, world):
     print(json.dumps(line))
 
 
+def _time_ms(fn, steps, warmup):
+    for w in range(warmup):
+        fn(w)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        fn(warmup + k)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def measure_reference_cuda_and_dropin(scene, cams, bg, cfg, dev, our_its, our_fps, steps=10, warmup=3):
+    """Rank 0, one GPU, outside every timed region of the headline numbers:
+    reference_cuda -- the reference's own kernels (oracle/_ref, recompiled for sm_100a) driven as
+                      scene/beta_model.py:660-711 drives them: frames/s, forward+backward it/s and our ratios to them;
+    dropin         -- the reference CALLER's statements (tests/ref_caller.py, AST-identical to BetaModel.render)
+                      against the gsplat shim: what a user who only swaps the import gets."""
+    from ubs_b200 import dropin, synth
+
+    W, H = cfg["width"], cfg["height"]
+    scene_d = scene.to(dev)
+    bg_d = bg.to(dev)
+    cams_d = [synth.Camera(c.viewmat.to(dev), c.K.to(dev), c.cam_pos.to(dev), c.width, c.height, c.timestamp)
+              for c in cams[:16]]
+    g = torch.Generator(device=dev).manual_seed(3)
+    v_img = torch.randn(3, H, W, device=dev, generator=g) / (W * H)
+    ref_line = {"unavailable": "oracle/_ref/ubs_ref_cuda.so not built"}
+    try:
+        from oracle import ref_cuda as ref
+
+        if ref.available():
+            v_rc = v_img.permute(1, 2, 0)[None].contiguous()
+            v_ra = torch.zeros(1, H, W, 1, device=dev)
+
+            def r_fwd(k):
+                cam = cams_d[k % len(cams_d)]
+                m, v, o, b0 = ref.condition(scene_d, cam)
+                ref.rasterization_fwd(m, v, o, b0, scene_d.rgb, cam.viewmat[None], cam.K[None], W, H,
+                                      backgrounds=bg_d[None])
+
+            ms_f = _time_ms(r_fwd, steps, warmup)
+            ms_t = _time_ms(lambda k: ref.chain_grads(scene_d, cams_d[k % len(cams_d)], bg_d, v_rc, v_ra), steps, warmup)
+            ref_line = {"frames_per_s": 1e3 / ms_f, "train_it_per_s": 1e3 / ms_t, "ms_per_frame": ms_f,
+                        "ms_per_fwdbwd": ms_t, "ratio": our_fps / (1e3 / ms_f), "train_ratio": our_its / (1e3 / ms_t),
+                        "steps": steps, "what": "reference gsplat CUDA kernels (oracle/_ref, sm_100a, the reference's "
+                        "flags) driven as scene/beta_model.py:660-711 drives them, same GPU, same scene and cameras; "
+                        "ratio = this library's 1-GPU-equivalent value / theirs"}
+            torch.cuda.empty_cache()
+    except Exception as e:  # the reference arm must never take the headline numbers down with it
+        ref_line = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    drop_line = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import ref_caller
+
+        model = ref_caller.BetaModelCaller(scene_d, bg_d, requires_grad=True)
+        vcs = [ref_caller.ViewpointCamera(c) for c in cams_d]
+
+        def d_fwd(k):
+            with torch.no_grad():
+                model.render(vcs[k % len(vcs)])
+
+        def d_train(k):
+            out = model.render(vcs[k % len(vcs)])
+            (out["render"] * v_img).sum().backward()
+            for t in model.leaves():
+                t.grad = None
+
+        s0 = dropin.stats()
+        ms_f = _time_ms(d_fwd, steps, warmup)
+        ms_t = _time_ms(d_train, steps, warmup)
+        s1 = dropin.stats()
+        drop_line = {"fwd_ms": ms_f, "fwdbwd_ms": ms_t, "fused_calls": s1["fused"] - s0["fused"],
+                     "fallback_calls": s1["fallback"] - s0["fallback"],
+                     "what": "BetaModel.render's statements (tests/ref_caller.py) + sum-loss backward to the seven "
+                             "leaf tensors through the gsplat import shim; includes torch's activations / cat / "
+                             "[mask] gathers of the caller and autograd's accumulation into the leaves"}
+        del model
+        torch.cuda.empty_cache()
+    except Exception as e:
+        drop_line = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    return ref_line, drop_line
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # this library
 # ----------------------------------------------------------------------------------------------------------------
@@ -282,21 +384,23 @@ def run_ours(args, rank, local_rank, world):
         trainer.step(rec, V[c:c + 1], K[c:c + 1], Cp[c:c + 1], None if Ts is None else Ts[c:c + 1], bgd, v_rc, v_ra,
                      v_rec)
 
+    sampler = ClockSampler(physical_gpu_index(local_rank))  # runs for the whole session; regions are cut out by time
+    sampler.start()
+
     def timed(fn, steps, warmup, with_stages):
         for w in range(warmup):
             fn(w)
         barrier()
         rz.enable_stage_timing(with_stages)
-        sampler = ClockSampler(physical_gpu_index(local_rank))
-        sampler.start()
         n0 = lib.ubs_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for k in range(steps):
             fn(warmup + k)
         e1.record()
         barrier()
-        clocks = sampler.stop()
+        clocks = sampler.region(t0, time.perf_counter())
         launches = lib.ubs_launch_count() - n0
         ms = e0.elapsed_time(e1)
         stages = rz.stage_times_ms() if with_stages else {}
@@ -356,8 +460,9 @@ def run_ours(args, rank, local_rank, world):
     ms_full, launches_full, clocks_full, stages_full = timed(train_full, args.steps, args.warmup, True)
     its_full = world * args.steps / (ms_full / 1e3)
     used_sharded = sharded is not None
-    del rec_train, tstep, sharded
+    del rec_train, tstep
     nccl_full = None
+    paths_check = None
     if world > 1:
         # the same step through NCCL: chunk-pipelined all-reduce of the gradient records + Adam on every rank
         rec_train = rec.clone()
@@ -366,6 +471,37 @@ def run_ours(args, rank, local_rank, world):
         nccl_full = {"value": world * args.steps / (ms_n / 1e3), "unit": "it/s", "ms_per_step": ms_n / args.steps,
                      "stages_ms": {k: v[1] for k, v in st_n.items()}}
         del rec_train, tstep
+        if sharded is not None:
+            # correctness of the default multi-GPU step, in the driver-visible line: three iterations of the sharded
+            # step and of the NCCL step from identical records and cameras; the parameters must agree (the two sum the
+            # ranks' gradients in different orders, so not bit for bit) and every rank must hold the same parameters
+            sharded.records.copy_(rec)
+            sharded.exp_avg.zero_()
+            sharded.exp_avg_sq.zero_()
+            sharded.barrier()
+            rec_n = rec.clone()
+            t_s = training.TrainStep(rz, training.PackedAdam(D, N, device=dev, allocate_moments=False), world=world,
+                                     sharded=sharded)
+            t_n = training.TrainStep(rz, training.PackedAdam(D, N, device=dev), world=world)
+            for k in range(3):
+                c = cam_of(k)
+                a = (V[c:c + 1], K[c:c + 1], Cp[c:c + 1], None if Ts is None else Ts[c:c + 1], bgd, gt_img)
+                t_s.step(sharded.records, *a, opacity_reg=0.01, scale_reg=0.01, batch_size=world)
+                t_n.step(rec_n, *a, opacity_reg=0.01, scale_reg=0.01, batch_size=world)
+            barrier()
+            d = (sharded.records - rec_n).abs()
+            moved = (rec_n - rec).abs().max()
+            stats = torch.stack([d.max(), (d > 1e-4).float().mean(), moved]).double()
+            dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+            chk = torch.stack([sharded.records.double().sum(), rec_n.double().sum()])
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            paths_check = {"iterations": 3, "sharded_vs_nccl_max_abs": float(stats[0]),
+                           "frac_entries_off_by_1e-4": float(stats[1]), "max_abs_parameter_change": float(stats[2]),
+                           "all_ranks_equal_sharded": bool(lo[0] == hi[0]), "all_ranks_equal_nccl": bool(lo[1] == hi[1])}
+            del rec_n, t_s, t_n
+    del sharded
 
     # ---- e2e: host buffers in, host image out, through the public API -----------------------------------------
     h_cam = torch.empty((N_RING, 16 + 9 + 3 + 1), dtype=torch.float32).pin_memory()
@@ -452,11 +588,22 @@ def run_ours(args, rank, local_rank, world):
     # SURVEY 8(d) unit figure: emit 12 B/pair + onesweep I (8 + 24 p) + offsets 8 B/pair.  The tile-binning route
     # this library runs (csrc/bin_sort.cu) moves 28 B/pair (8 written, 8 read, 12 written) and is bound by the
     # ranking instructions of its per-tile shared-memory sort, not by HBM; both figures are reported.
-    hbm_stage("isect_emit_sort_offsets", stages.get("isect_emit_sort_offsets", (0, float("nan")))[1],
-              pairs * (12 + 8 + 24 * passes + 8))
-    if "isect_emit_sort_offsets" in stage_roof:
-        stage_roof["isect_emit_sort_offsets"]["route"] = rz.sort_mode
-        stage_roof["isect_emit_sort_offsets"]["bytes_moved_by_bin_route"] = pairs * 28
+    sort_ms = stages.get("isect_emit_sort_offsets", (0, float("nan")))[1]
+    if rz.sort_mode == "bin":
+        # bytes this route moves: 8 B/pair written by the emit, 8 read + 12 written by the per-tile sort.  It is NOT
+        # HBM bound (the 50 MB of pairs stay in L2): the emit is bound by L2 atomic throughput, the per-tile sort by
+        # instruction issue and dependent shared-memory latency (ncu) -- frac is bytes moved / time / peak
+        hbm_stage("isect_emit_sort_offsets", sort_ms, pairs * 28)
+        if "isect_emit_sort_offsets" in stage_roof:
+            stage_roof["isect_emit_sort_offsets"].update(
+                bound="l2-atomics + issue (not hbm)", route="bin",
+                survey_unit_bytes_onesweep=pairs * (12 + 8 + 24 * passes + 8),
+                note="frac = bytes actually moved / time / HBM peak; the SURVEY 8(d) unit (emit 12 + onesweep "
+                     "8 + 24 p + offsets 8 B/pair) describes the onesweep route, which this route replaces")
+    else:
+        hbm_stage("isect_emit_sort_offsets", sort_ms, pairs * (12 + 8 + 24 * passes + 8))
+        if "isect_emit_sort_offsets" in stage_roof:
+            stage_roof["isect_emit_sort_offsets"]["route"] = rz.sort_mode
     hbm_stage("fused_project_bwd", stages_train.get("fused_project_bwd", (0, float("nan")))[1],
               2 * N * rec_b + vis * 76)
     stage_roof["rasterize_bwd"] = {"bound": "fp32", "ms": stages_train.get("rasterize_bwd", (0, float("nan")))[1],
@@ -472,6 +619,9 @@ def run_ours(args, rank, local_rank, world):
     if rb["ms"] == rb["ms"] and rb["ms"] > 0:
         rb["achieved"] = rb["slots"] / (rb["ms"] * 1e-3) / 1e12
         rb["peak"], rb["unit"], rb["frac"] = fp32_peak, "Tinstr/s", rb["slots"] / (rb["ms"] * 1e-3) / 1e12 / fp32_peak
+
+    # ---- the number to beat: the reference's own CUDA kernels on this GPU, and the zero-edit drop-in -------------
+    ref_cuda_line, dropin_line = measure_reference_cuda_and_dropin(scene, cams, bg, cfg, dev, its / world, fps / world)
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample --------------------------------
     cpu = None
@@ -520,7 +670,13 @@ def run_ours(args, rank, local_rank, world):
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": "fused.HostPipeline.render_to_host: pinned host camera -> device, render, FP32 RGB image -> "
                         "pinned host, double-buffered; wall clock over the timed steps"},
-        "gpu_launches": launches, "clocks": clocks,
+        "gpu_launches": launches, "clocks": clocks, "clocks_session": sampler.stop(),
+        # ---- the last keys: what a reader of the tail of this line needs ----------------------------------------------
+        "train_full_summary": {"value": its_full, "unit": "it/s", "ms_per_step": ms_full / args.steps,
+                               "stages_ms": {k: round(v[1], 4) for k, v in stages_full.items()},
+                               "nccl_path_it_per_s": None if nccl_full is None else nccl_full["value"],
+                               "paths_check": paths_check},
+        "reference_cuda": ref_cuda_line, "dropin": dropin_line,
     }
     print(json.dumps(line))
     if world > 1:

@@ -362,9 +362,12 @@ int ubs_reduce_adam_gather(int64_t N, int D, int world, int rank, int64_t shard_
  * 1 - (1 - o)^(1/(m+1)), m = multiplicity of the source among src_idx, clamped to [0.005, 1 - eps]; the sources
  * take the same opacity and their Adam moments are zeroed (exp_avg / exp_avg_sq may both be NULL).
  * replaces the tensor part of relocate_gs / add_new_gs (scene/beta_model.py:512-657); dst and src rows must be
- * disjoint sets (dead vs alive primitives, or freshly appended rows).  counts: [N] int32 scratch.            */
-int ubs_mcmc_relocate(int64_t N, int D, float *records, float *exp_avg, float *exp_avg_sq, int64_t K,
-                      const int64_t *dst_idx, const int64_t *src_idx, int32_t *counts, void *stream);
+ * disjoint sets (dead vs alive primitives, or freshly appended rows).  counts: [N] int32 scratch.  The moment
+ * buffers hold rows [moment_row_begin, moment_row_begin + moment_row_count): (0, N) for whole-buffer moments, the
+ * rank's own shard in the sharded step (sources outside it are some other rank's to reset).                    */
+int ubs_mcmc_relocate(int64_t N, int D, float *records, float *exp_avg, float *exp_avg_sq, int64_t moment_row_begin,
+                      int64_t moment_row_count, int64_t K, const int64_t *dst_idx, const int64_t *src_idx,
+                      int32_t *counts, void *stream);
 
 /* SGLD position noise of the MCMC densification step (train.py:156-163): xyz += Sigma_xyz (noise (1 - sigmoid(raw
  * opacity))^100 noise_lr xyz_lr), Sigma_xyz = BetaModel.get_xyz_covariance (scene/beta_model.py:143-152, the

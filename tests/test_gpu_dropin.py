@@ -62,6 +62,13 @@ def test_reference_caller_statements_take_the_fused_route(D, N, W, H, monkeypatc
             return inner(*a, **kw)
 
     monkeypatch.setattr(rc_mod, "rasterization", guarded)
+    inner_bwd = dropin._DropinRender.backward
+
+    def guarded_bwd(ctx, *grads):  # likewise the route's autograd node (the caller's `[mask]` backward does synchronise)
+        with _NoSync():
+            return inner_bwd(ctx, *grads)
+
+    monkeypatch.setattr(dropin._DropinRender, "backward", staticmethod(guarded_bwd))
     before = dropin.stats()
     out = model.render(vc)
     after = dropin.stats()
@@ -83,8 +90,7 @@ def test_reference_caller_statements_take_the_fused_route(D, N, W, H, monkeypatc
 
     g = torch.Generator(device="cuda").manual_seed(5)
     v_img = torch.randn(3, H, W, device="cuda", generator=g) / (H * W)
-    with _NoSync():
-        (out["render"] * v_img).sum().backward()
+    (out["render"] * v_img).sum().backward()
     v_rc = v_img.permute(1, 2, 0)[None].contiguous()
     ref_grads, _ = ref.chain_grads(scene, rcam, bg, v_rc, torch.zeros(1, H, W, 1, device="cuda"))
     for nm, leaf, want in zip(("xyz", "mean", "rgb", "opacity", "beta", "scale", "l_triangle"), model.leaves(), ref_grads):
@@ -211,13 +217,14 @@ def test_viewer_call_with_quantile_mask_takes_the_fused_route(mode):
         want = depth_img / R["render_alphas"].clamp(min=1e-10)
         torch.testing.assert_close(img[..., 3:][ok], want[ok], rtol=1e-3, atol=1e-3)
     else:  # Normal: the reference's depth_to_normal on the reference depth image, mapped to [0, 1]
+        from test_gpu_pinned import _well_conditioned_normals
+
         want = (rendering.depth_to_normal(depth_img, c2w[None], cam.K[None]) + 1) / 2
         assert img.shape == (1, H, W, 3)
-        # normals of nearly-empty pixels are the direction of a tiny vector: compare where the depth surface is real
-        solid = (R["render_alphas"][..., 0] > 0.9)
-        solid = solid & solid.roll(1, 1) & solid.roll(-1, 1) & solid.roll(1, 2) & solid.roll(-1, 2)
-        assert solid.float().mean() > 0.01
-        assert ((img - want).abs().max(dim=-1).values[solid] < 2e-2).float().mean() > 0.98
+        # compare where the normal is not the direction of a near-zero vector
+        well = _well_conditioned_normals(depth_img, c2w[None], cam.K[None])
+        assert well.float().mean() > 0.05
+        assert ((img - want).abs().max(dim=-1).values[well] < 2e-2).float().mean() > 0.98
 
 
 def test_flatten_ids_of_a_filtered_view_index_the_kept_primitives():

@@ -217,7 +217,7 @@ def test_splat_rows_equal_the_separate_arrays_and_both_compositing_entries_agree
         if use_splats:
             check(lib.ubs_rasterize_bwd_splats(1, N, ptr(rz.n_isects), rz.capacity, ptr(rz.splats), ptr(colors), ptr(bg), None,
                                                3, W, H, 16, ptr(rz.offsets), ptr(rz.flatten_ids), ptr(rz.render_alphas),
-                                               ptr(rz.last_ids), ptr(v_rc), ptr(v_ra), *[ptr(t) for t in out], s), "bwd_splats")
+                                               ptr(rz.last_ids), ptr(v_rc), ptr(v_ra), *[ptr(t) for t in out], None, s), "bwd_splats")
         else:
             check(lib.ubs_rasterize_bwd(1, N, ptr(rz.n_isects), rz.capacity, ptr(rz.means2d), ptr(rz.conics), ptr(rz.colors),
                                         ptr(rz.opacities), ptr(rz.betas), ptr(bg), None, 3, W, H, 16, ptr(rz.offsets),

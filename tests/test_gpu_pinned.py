@@ -149,6 +149,21 @@ def test_tile_masks_forward_and_backward_match_reference_kernels():
         _assert_grad_close(name, a, b)
 
 
+def _well_conditioned_normals(depth_img, c2w, Ks, noise=1e-4):
+    """Pixels whose normal (direction of a cross product of depth differences) moves by < 5e-3 under the 1e-4
+    depth noise the image tolerance allows: elsewhere the normal is the direction of a near-zero vector."""
+    from ubs_b200 import rendering
+
+    g = torch.Generator(device=depth_img.device).manual_seed(0)
+    scale = max(float(depth_img.abs().max()), 1.0)
+    n0 = rendering.depth_to_normal(depth_img, c2w, Ks)
+    worst = torch.zeros_like(n0[..., 0])
+    for _ in range(3):
+        d = depth_img + noise * scale * (2 * torch.rand(depth_img.shape, device=depth_img.device, generator=g) - 1)
+        worst = torch.maximum(worst, (rendering.depth_to_normal(d, c2w, Ks) - n0).abs().max(dim=-1).values)
+    return (worst < 1e-2) & (n0.norm(dim=-1) > 0.5)
+
+
 # ---- depth-channel values through the operator chain ----------------------------------------------------------------------
 @pytest.mark.parametrize("mode", ["RGB+D", "RGB+ED", "Depth", "EDepth", "Normal"])
 def test_depth_channel_values_of_rasterization(mode):
@@ -176,11 +191,11 @@ def test_depth_channel_values_of_rasterization(mode):
         want = acc / P["render_alphas"].clamp(min=1e-10)
         torch.testing.assert_close(rc[..., 3:][ok], want[ok], rtol=1e-3, atol=1e-3)
     else:
-        want = (rendering.depth_to_normal(acc, torch.inverse(viewmats), Ks) + 1) / 2
-        solid = P["render_alphas"][..., 0] > 0.9
-        solid = solid & solid.roll(1, 1) & solid.roll(-1, 1) & solid.roll(1, 2) & solid.roll(-1, 2)
-        assert solid.float().mean() > 0.01
-        assert ((rc - want).abs().max(dim=-1).values[solid] < 2e-2).float().mean() > 0.98
+        c2w = torch.inverse(viewmats)
+        want = (rendering.depth_to_normal(acc, c2w, Ks) + 1) / 2
+        well = _well_conditioned_normals(acc, c2w, Ks)
+        assert well.float().mean() > 0.05
+        assert ((rc - want).abs().max(dim=-1).values[well] < 2e-2).float().mean() > 0.98
 
 
 @pytest.mark.parametrize("channels", [4, 1])
@@ -227,7 +242,7 @@ def test_fused_depth_channel_backward_matches_reference_kernels(channels):
     g_m3_nod, _, _, _, _ = C_.fully_fused_projection_bwd(m, cov6, None, None, cam.viewmat[None], cam.K[None], W, H, 0.3,
                                                          False, P["radii"], P["conics"], None, g2d,
                                                          torch.zeros_like(v_depths), gcon, None, False)
-    assert float((g_m3 - g_m3_nod).abs().max()) > 1e-2 * float(g_m3.abs().max())
+    assert float((g_m3 - g_m3_nod).abs().max()) > 2e-3 * float(g_m3.abs().max())
 
 
 # ---- guards of the fused rasteriser ------------------------------------------------------------------------------------

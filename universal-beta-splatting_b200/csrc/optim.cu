@@ -123,16 +123,17 @@ relocate_copy_kernel(int64_t K, int stride, int col_opacity, float *__restrict__
 __global__ void __launch_bounds__(256)
 relocate_fixup_kernel(int64_t K, int stride, int col_opacity, float *__restrict__ records,
                       float *__restrict__ exp_avg, float *__restrict__ exp_avg_sq, const int64_t *__restrict__ dst,
-                      const int64_t *__restrict__ src) {
+                      const int64_t *__restrict__ src, int64_t m_begin, int64_t m_count) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= K) return;
     const int64_t s = src[i], d = dst[i];
     if (lane == 0) records[s * stride + col_opacity] = records[d * stride + col_opacity];
-    if (exp_avg != nullptr)
+    // the moment buffers hold rows [m_begin, m_begin + m_count) (all rows, or this rank's shard of the sharded step)
+    if (exp_avg != nullptr && s >= m_begin && s < m_begin + m_count)
         for (int c = lane; c < stride; c += 32) {
-            exp_avg[s * stride + c] = 0.f;
-            exp_avg_sq[s * stride + c] = 0.f;
+            exp_avg[(s - m_begin) * stride + c] = 0.f;
+            exp_avg_sq[(s - m_begin) * stride + c] = 0.f;
         }
 }
 
@@ -209,7 +210,8 @@ extern "C" int ubs_adam_step(int64_t N, int D, int64_t row_begin, int64_t row_co
     return UBS_OK;
 }
 
-extern "C" int ubs_mcmc_relocate(int64_t N, int D, float *records, float *exp_avg, float *exp_avg_sq, int64_t K,
+extern "C" int ubs_mcmc_relocate(int64_t N, int D, float *records, float *exp_avg, float *exp_avg_sq,
+                                 int64_t moment_row_begin, int64_t moment_row_count, int64_t K,
                                  const int64_t *dst_idx, const int64_t *src_idx, int32_t *counts, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(N >= 0 && K >= 0 && D >= 4 && D <= 8, "mcmc_relocate: bad sizes");
@@ -224,7 +226,8 @@ extern "C" int ubs_mcmc_relocate(int64_t N, int D, float *records, float *exp_av
     const unsigned grid = (unsigned)ceil_div(K * 32, 256);
     relocate_copy_kernel<<<grid, 256, 0, s>>>(K, stride, col_opacity, records, dst_idx, src_idx, counts);
     UBS_LAUNCH_CHECK("relocate_copy_kernel");
-    relocate_fixup_kernel<<<grid, 256, 0, s>>>(K, stride, col_opacity, records, exp_avg, exp_avg_sq, dst_idx, src_idx);
+    relocate_fixup_kernel<<<grid, 256, 0, s>>>(K, stride, col_opacity, records, exp_avg, exp_avg_sq, dst_idx, src_idx,
+                                               moment_row_begin, moment_row_count);
     UBS_LAUNCH_CHECK("relocate_fixup_kernel");
     return UBS_OK;
 }

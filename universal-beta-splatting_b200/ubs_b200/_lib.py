@@ -65,7 +65,7 @@ SIGNATURES = {
                                       [_P] * 8 + [c_int, c_int, c_int64, _P, _P, _P]),
     "ubs_reduce_adam_gather": (c_int, [c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P, c_double, c_double,
                                        c_double, c_int64, c_double, c_double, _P]),
-    "ubs_mcmc_relocate": (c_int, [c_int64, c_int, _P, _P, _P, c_int64, _P, _P, _P, _P]),
+    "ubs_mcmc_relocate": (c_int, [c_int64, c_int, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
     "ubs_sgld_noise": (c_int, [c_int64, c_int, _P, _P, c_double, c_double, _P]),
 }
 

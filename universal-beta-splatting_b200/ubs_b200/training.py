@@ -182,22 +182,29 @@ class PackedAdam:
 
 
 @torch.no_grad()
-def mcmc_relocate(records: Tensor, D: int, dst_idx: Tensor, src_idx: Tensor, adam: Optional[PackedAdam] = None):
+def mcmc_relocate(records: Tensor, D: int, dst_idx: Tensor, src_idx: Tensor, adam: Optional[PackedAdam] = None,
+                  sharded=None):
     """Rows dst_idx <- rows src_idx with the multiplicity-rescaled opacity; sources take the same opacity and lose
     their Adam moments.  With dst = dead primitives and src = torch.multinomial samples of the alive ones this is
-    relocate_gs (scene/beta_model.py:575-620)."""
+    relocate_gs (scene/beta_model.py:575-620).  Moments: `adam`'s whole-buffer ones, or -- sharded step -- the shard
+    of a parallel.ShardedState (every rank calls this with the same indices and resets the sources it owns)."""
     lib = _lib.load()
     N, K = records.shape[0], dst_idx.numel()
     assert src_idx.numel() == K and dst_idx.dtype == torch.int64 and src_idx.dtype == torch.int64
     if K == 0:
         return
+    m, v, m_begin, m_count = None, None, 0, N
+    if sharded is not None:
+        m, v = sharded.exp_avg, sharded.exp_avg_sq
+        m_begin, m_count = sharded.rank * sharded.shard_rows, sharded.shard_rows
+    elif adam is not None and adam.exp_avg.shape[0] == N:
+        m, v = adam.exp_avg, adam.exp_avg_sq
     counts = torch.empty((N,), dtype=torch.int32, device=records.device)
     # bound to locals: a .contiguous() copy must stay alive until after the launch (a temporary's block would be
     # handed to the next same-sized allocation, and both pointers would name the same memory)
     dst_c, src_c = dst_idx.contiguous(), src_idx.contiguous()
-    check(lib.ubs_mcmc_relocate(N, D, ptr(records), ptr(adam.exp_avg) if adam else None,
-                                ptr(adam.exp_avg_sq) if adam else None, K, ptr(dst_c), ptr(src_c), ptr(counts),
-                                torch.cuda.current_stream().cuda_stream),
+    check(lib.ubs_mcmc_relocate(N, D, ptr(records), ptr(m), ptr(v), m_begin, m_count, K, ptr(dst_c), ptr(src_c),
+                                ptr(counts), torch.cuda.current_stream().cuda_stream),
           "ubs_mcmc_relocate")
 
 
@@ -243,20 +250,26 @@ def sample_alive(probs: Tensor, num: int, alive_indices: Optional[Tensor] = None
 
 
 class TrainStep:
-    """One full training iteration of one view per GPU on resident buffers:
-    forward -> L1+SSIM loss and its image gradient -> backward -> (all-reduce) -> Adam.  Zero host syncs."""
+    """One full training iteration on resident buffers, zero host syncs:
+    forward -> L1+SSIM loss and its image gradient -> backward -> (all-reduce) -> Adam.
+
+    The rasteriser's camera count C is the per-GPU batch: train.py:111-128 renders `batch_size` views, averages their
+    losses, calls backward() once and steps the optimiser once -- here the C views are rendered by ONE launch sequence,
+    the loss kernel averages over the C images, the projection backward sums the per-camera gradients in registers,
+    and there is one update.  With `world` ranks the effective batch is C * world (pass it as `batch_size`)."""
 
     def __init__(self, rz: FusedRasterizer, adam: PackedAdam, lambda_dssim: float = 0.2, world: int = 1, group=None,
                  fuse_adam: bool = True, n_chunks: int = 4, sharded=None):
-        assert rz.C == 1
-        self.n_chunks = n_chunks
+        assert sharded is None or rz.C == 1, "the sharded step scatters one view per rank"
+        # row-range pipelining of the projection backward against the all-reduce needs [1, N] screen-space arrays
+        self.n_chunks = n_chunks if rz.C == 1 else 1
         # sharded: a parallel.ShardedState -- gradient tiles go over NVLink into the owner rank's staging buffer
         # straight from the projection-backward kernel, the owner reduces + applies Adam to its 1/world of the rows
         # and stores the new parameters into every rank's records; `records` passed to step() must be sharded.records
         self.sharded = sharded
         self.rz, self.adam, self.lam, self.world, self.group = rz, adam, lambda_dssim, world, group
-        # one view per optimiser step on one GPU (the reference's default batch_size = 1): nothing to sum before the
-        # update, so Adam rides in the projection-backward kernel and the gradient records never reach HBM
+        # nothing to sum across ranks before the update on one GPU (the reference's default set-up): Adam rides in the
+        # projection-backward kernel and the gradient records never reach HBM
         self.fuse_adam = fuse_adam
         dev = rz.device
         self.v_rc = torch.empty_like(rz.render_colors)
@@ -266,11 +279,20 @@ class TrainStep:
 
     @torch.no_grad()
     def step(self, records: Tensor, viewmats, Ks, cam_pos, timestamps, backgrounds, gt: Tensor, gt_layout="NCHW",
-             opacity_reg: float = 0.0, scale_reg: float = 0.0, batch_size: int = 1) -> Tensor:
+             opacity_reg: float = 0.0, scale_reg: float = 0.0, batch_size: Optional[int] = None,
+             apply_update: bool = True) -> Tensor:
+        """gt: [C,3,H,W] (or [3,H,W] for C = 1).  batch_size: views per optimiser step over all ranks (default
+        C * world); each rank's loss is the mean over its C views scaled by C / batch_size.
+        apply_update=False: forward, loss and backward only -- the gradient records are left in `self.v_records`, the
+        parameters, the moments and the step count stay untouched.  (On its densification iterations the reference
+        swaps fresh nn.Parameters into the optimiser BEFORE optimizer.step(), so that step finds no gradients and is
+        skipped, train.py:150-169 / scene/beta_model.py:512-546: a caller reproducing that ordering passes False.)"""
         from . import parallel
 
         rz = self.rz
-        fused_update = self.fuse_adam and self.world == 1 and self.sharded is None
+        C = rz.C
+        batch_size = C * self.world if batch_size is None else batch_size
+        fused_update = self.fuse_adam and self.world == 1 and self.sharded is None and apply_update
         if not fused_update and self.sharded is None and (self.v_records is None or
                                                           self.v_records.shape != records.shape):
             self.v_records = torch.empty_like(records)
@@ -278,10 +300,18 @@ class TrainStep:
         if gt.dim() == 3:
             gt = gt.unsqueeze(0)
         with rz._stage("l1_ssim_loss"):
-            l1_ssim_loss_fwd_bwd(rc, gt, self.lam, 1.0 / batch_size, "NHWC", gt_layout, True, self.v_rc, self.loss_out)
+            # the kernel's loss is the mean over the C images; d(C / batch_size * that) reaches the renderer
+            l1_ssim_loss_fwd_bwd(rc, gt, self.lam, float(C) / batch_size, "NHWC", gt_layout, True, self.v_rc,
+                                 self.loss_out)
         if fused_update:
             rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, self.v_rc, self.v_ra, None, self.adam,
                         opacity_reg, scale_reg)
+            return self.loss_out
+        if not apply_update:
+            assert self.sharded is None, "apply_update=False needs a local gradient buffer (not the sharded step)"
+            rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, self.v_rc, self.v_ra, self.v_records)
+            if self.world > 1:
+                parallel.allreduce_gradients(self.v_records, self.world, None, self.group)
             return self.loss_out
         if self.sharded is not None:
             st = self.sharded
@@ -296,8 +326,8 @@ class TrainStep:
             with rz._stage("barrier"):
                 st.barrier()  # every shard's new parameters have landed in my records
             return self.loss_out
-        # world > 1: the projection backward runs chunk by chunk; chunk k's gradient all-reduce (NCCL, its own stream)
-        # overlaps the backward of chunk k+1 and the Adam update of chunk k-1
+        # world > 1, or the unfused single-GPU form: the projection backward runs chunk by chunk; chunk k's gradient
+        # all-reduce (NCCL, its own stream) overlaps the backward of chunk k+1 and the Adam update of chunk k-1
         adam, first = self.adam, [True]
 
         def after_reduce(begin, count):
