@@ -343,6 +343,11 @@ def run_ours(args, rank, local_rank, world):
     from ubs_b200 import _lib, fused, parallel
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
+    # pinned host buffers (the e2e path) should sit on the NUMA node of this rank's GPU: bind before anything is pinned
+    from ubs_b200 import hostmem
+
+    affinity_before = os.sched_getaffinity(0)
+    numa = hostmem.bind_to_gpu_node(physical_gpu_index(local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()
@@ -509,7 +514,7 @@ def run_ours(args, rank, local_rank, world):
     h_cam[:, 16:25] = torch.stack([c.K for c in cams]).reshape(N_RING, 9)
     h_cam[:, 25:28] = torch.stack([c.cam_pos for c in cams])
     h_cam[:, 28] = torch.tensor([c.timestamp for c in cams])
-    pipe = fused.HostPipeline(rz, depth=2)
+    pipe = fused.HostPipeline(rz, depth=3)
 
     def e2e(step):
         pipe.render_to_host(rec, h_cam[cam_of(step)], bgd)
@@ -532,6 +537,10 @@ def run_ours(args, rank, local_rank, world):
     h2d = h_cam[0].numel() * 4
     d2h = P * 3 * 4  # the FP32 RGB image (what BetaModel.view returns to the host)
 
+    try:
+        os.sched_setaffinity(0, affinity_before)  # the CPU baseline below uses every host core
+    except Exception:
+        pass
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -669,7 +678,8 @@ def run_ours(args, rank, local_rank, world):
         "work": counts, "cpu_baseline": cpu,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": "fused.HostPipeline.render_to_host: pinned host camera -> device, render, FP32 RGB image -> "
-                        "pinned host, double-buffered; wall clock over the timed steps"},
+                        "pinned host, three frames in flight; wall clock over the timed steps",
+                "host_placement": numa},
         "gpu_launches": launches, "clocks": clocks, "clocks_session": sampler.stop(),
         # ---- the last keys: what a reader of the tail of this line needs ----------------------------------------------
         "train_full_summary": {"value": its_full, "unit": "it/s", "ms_per_step": ms_full / args.steps,
