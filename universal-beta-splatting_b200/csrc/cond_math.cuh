@@ -23,9 +23,17 @@ struct NdDims {
 __device__ __host__ constexpr int tril_idx(int r, int k) { return r * (r - 1) / 2 + k; }
 
 // ---- activations (scene/beta_model.py:36-52) ----------------------------------------------------------------
-__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // F.softplus
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
-__device__ __forceinline__ float beta_act_f(float x) { return 4.f * expf(x); }
+// The reference applies them with torch (F.softplus, torch.sigmoid, 4 * torch.exp), whose CUDA kernels are built
+// WITHOUT fast-math: libdevice's full-precision expf / log1pf and IEEE division.  This library is a --use_fast_math
+// build (the reference's own kernels are, and the tile lists must match bit for bit), under which `expf` would be
+// ex2.approx -- enough to move a radius across an integer boundary for a few primitives in a million.  So the precise
+// libdevice entry points are named explicitly: activated values are bit-identical to torch's, and with them every
+// integer output of the fused path (radii, tile counts, sorted pair lists) equals the reference chain's.
+extern "C" __device__ float __nv_expf(float);
+extern "C" __device__ float __nv_log1pf(float);
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : __nv_log1pf(__nv_expf(x)); }  // F.softplus
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, __nv_expf(-x))); }
+__device__ __forceinline__ float beta_act_f(float x) { return __fmul_rn(4.f, __nv_expf(x)); }
 
 // ---- K1 + K2: L and Sigma = L L^T -----------------------------------------------------------------------------
 // L is the full D x D lower-triangular factor: L[:3,:3] = R diag(s0..s2) (R = any 3x3, row-major),

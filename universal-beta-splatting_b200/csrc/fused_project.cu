@@ -61,6 +61,14 @@ struct PrimState {
     CondPrep<C> prep;
 };
 
+// |v| exactly as torch computes `view_dir.norm(dim=-1)` on CUDA (scene/beta_model.py:677): its reduction kernel gives a
+// size-3 row to TWO threads -- one squares and adds elements 0 and 2, the other squares element 1 -- and then adds the
+// partial sums: sqrt((x^2 + z^2) + y^2), every operation rounded to FP32 (3,000,000 of 3,000,000 norms bit-equal on
+// the B200 box against 88.7 % for the left-to-right order, scratch/norm_order.py); IEEE sqrt and division, as ATen's.
+__device__ __forceinline__ float view_norm(float dx, float dy, float dz) {
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dz, dz)), __fmul_rn(dy, dy)));
+}
+
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // `activated`: the record already holds the ACTIVATED values (softplus'd scales, sigmoid'd opacity, 4 exp'd betas), as
@@ -172,7 +180,7 @@ fused_project_fwd_kernel(int C, int64_t N, const float *__restrict__ records, co
             } else {
                 const float dx = ps.xyz[0] - cam_pos[cid * 3 + 0], dy = ps.xyz[1] - cam_pos[cid * 3 + 1],
                             dz = ps.xyz[2] - cam_pos[cid * 3 + 2];
-                const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+                const float nrm = view_norm(dx, dy, dz);
                 x[0] = __fdiv_rn(dx, nrm) - ps.mu2[0];
                 x[1] = __fdiv_rn(dy, nrm) - ps.mu2[1];
                 x[2] = __fdiv_rn(dz, nrm) - ps.mu2[2];
@@ -429,7 +437,7 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
             } else {
                 const float dx = xyz[0] - cam_pos[cid * 3 + 0], dy = xyz[1] - cam_pos[cid * 3 + 1],
                             dz = xyz[2] - cam_pos[cid * 3 + 2];
-                const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+                const float nrm = view_norm(dx, dy, dz);
                 x[0] = __fdiv_rn(dx, nrm) - mu2[0];
                 x[1] = __fdiv_rn(dy, nrm) - mu2[1];
                 x[2] = __fdiv_rn(dz, nrm) - mu2[2];
