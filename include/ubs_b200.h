@@ -252,7 +252,9 @@ int ubs_fused_project_fwd(int C, int64_t N, int D, const float *records, /* [N, 
                           int32_t *radii,           /* [C,N]   */
                           float *means2d,           /* [C,N,2] */
                           float *depths,            /* [C,N]   */
-                          float *conics,            /* [C,N,3] */
+                          float *conics,            /* [C,N,3]; NULL = render-only frame: conics, opacities, betas,
+                                                       colors and tiles_per_gauss are not written (the compositing
+                                                       kernels gather from `splats`; no backward, no `meta`) */
                           float *opacities,         /* [C,N] conditioned (x compensation if requested) */
                           float *betas,             /* [C,N] spatial beta = 4 exp(raw beta_0) */
                           float *colors,            /* [C,N,3] or NULL (rgb copied out of the record) */

@@ -239,3 +239,46 @@ def test_splat_rows_equal_the_separate_arrays_and_both_compositing_entries_agree
                                        W, H, 16, ptr(rz.offsets), ptr(rz.flatten_ids), ptr(rc3), ptr(ra3), ptr(last3), s),
           "fwd_splats")
     assert torch.equal(rc3, rc) and torch.equal(ra3, ra) and torch.equal(last3, rz.last_ids)
+
+
+def test_render_only_frames_render_queue_and_host_pipeline_match_plain_forward():
+    """screen_space=False skips the arrays only `meta` / backward read; RenderQueue and a two-rasteriser HostPipeline
+    run frames on several streams.  All of them must give bit-identical images."""
+    from ubs_b200 import fused, synth
+
+    D, N, W, H = 6, 40000, 400, 304
+    scene = synth.make_scene(N, D, seed=77).to("cuda")
+    cams = synth.make_cameras(5, W, H, seed=5, device="cuda")
+    bg = torch.tensor([[0.2, 0.1, 0.4]], device="cuda")
+    rec = fused.pack_records(D, *scene.tensors())
+    plain = fused.FusedRasterizer(D, N, W, H)
+    want = []
+    for c in cams:
+        rc, ra = plain.forward(rec, c.viewmat[None], c.K[None], c.cam_pos[None], None, bg)
+        want.append((rc.clone(), ra.clone()))
+    rz = fused.FusedRasterizer(D, N, W, H)
+    for c, (rc0, ra0) in zip(cams, want):
+        rz.conics.fill_(float("nan"))
+        rc, ra = rz.forward(rec, c.viewmat[None], c.K[None], c.cam_pos[None], None, bg, screen_space=False)
+        assert torch.equal(rc, rc0) and torch.equal(ra, ra0)
+        assert bool(torch.isnan(rz.conics).all()), "render-only frame wrote the separate arrays"
+    with pytest.raises(AssertionError):
+        rz.backward(rec, cams[0].viewmat[None], cams[0].K[None], cams[0].cam_pos[None], None, bg, rc, ra)
+    made = []
+    queue = fused.RenderQueue(lambda: made.append(fused.FusedRasterizer(D, N, W, H)) or made[-1], depth=2)
+    outs = []
+    for c in cams:
+        slot, rc, ra = queue.render(rec, c.viewmat[None], c.K[None], c.cam_pos[None], None, bg, screen_space=False)
+        queue.wait(slot)
+        outs.append((rc.clone(), ra.clone()))
+    for (rc, ra), (rc0, ra0) in zip(outs, want):
+        assert torch.equal(rc, rc0) and torch.equal(ra, ra0)
+    pipe = fused.HostPipeline(made, depth=3)
+    rows = torch.empty((len(cams), fused.HostPipeline.CAM_FLOATS)).pin_memory()
+    for k, c in enumerate(cams):
+        rows[k] = torch.cat([c.viewmat.reshape(-1), c.K.reshape(-1), c.cam_pos, torch.zeros(1, device="cuda")]).cpu()
+    for k in range(len(cams)):
+        slot = pipe.render_to_host(rec, rows[k], bg)
+        host_rc, _ = pipe.wait(slot)
+        assert torch.equal(host_rc, want[k][0].cpu())
+    pipe.drain()

@@ -34,6 +34,11 @@ extern "C" __device__ float __nv_log1pf(float);
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : __nv_log1pf(__nv_expf(x)); }  // F.softplus
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, __nv_expf(-x))); }
 __device__ __forceinline__ float beta_act_f(float x) { return __fmul_rn(4.f, __nv_expf(x)); }
+// The backward pass recomputes the activated values only to evaluate derivatives (FP32 tolerance, no integer decided
+// by them): there the fast-math forms are used -- 35 us of a 0.39 ms kernel at 3M primitives.
+__device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float beta_act_fast(float x) { return 4.f * expf(x); }
 
 // ---- K1 + K2: L and Sigma = L L^T -----------------------------------------------------------------------------
 // L is the full D x D lower-triangular factor: L[:3,:3] = R diag(s0..s2) (R = any 3x3, row-major),

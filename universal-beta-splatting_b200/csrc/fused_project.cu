@@ -208,17 +208,21 @@ fused_project_fwd_kernel(int C, int64_t N, const float *__restrict__ records, co
         radii[idx] = o.radius;
         reinterpret_cast<float2 *>(means2d)[idx] = make_float2(o.mean2d[0], o.mean2d[1]);
         depths[idx] = o.depth;
-        conics[idx * 3 + 0] = o.conic[0];
-        conics[idx * 3 + 1] = o.conic[1];
-        conics[idx * 3 + 2] = o.conic[2];
-        opacities[idx] = o.radius > 0 ? opac : 0.f;
-        betas[idx] = active ? ps.beta0 : 0.f;
-        if (colors != nullptr) {
-            colors[idx * 3 + 0] = active ? ps.rgb[0] : 0.f;
-            colors[idx * 3 + 1] = active ? ps.rgb[1] : 0.f;
-            colors[idx * 3 + 2] = active ? ps.rgb[2] : 0.f;
+        // the rest of the separate arrays is what `meta` and the projection backward read; a render-only frame
+        // (conics == NULL) composites from the splat rows alone and saves 36 bytes of writes per primitive
+        if (conics != nullptr) {
+            conics[idx * 3 + 0] = o.conic[0];
+            conics[idx * 3 + 1] = o.conic[1];
+            conics[idx * 3 + 2] = o.conic[2];
+            opacities[idx] = o.radius > 0 ? opac : 0.f;
+            betas[idx] = active ? ps.beta0 : 0.f;
+            if (colors != nullptr) {
+                colors[idx * 3 + 0] = active ? ps.rgb[0] : 0.f;
+                colors[idx * 3 + 1] = active ? ps.rgb[1] : 0.f;
+                colors[idx * 3 + 2] = active ? ps.rgb[2] : 0.f;
+            }
+            tiles_per_gauss[idx] = cnt;
         }
-        tiles_per_gauss[idx] = cnt;
         // the same screen-space record once more as ONE 48-byte row for the compositing kernels: their per-pair gather
         // then touches two sectors instead of five (the compositing forward is L1-sensitive: 0.62 -> 0.53 ms)
         if (splats != nullptr && o.radius > 0) {
@@ -385,12 +389,12 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
         for (int k = 0; k < 3; ++k) xyz[k] = rec[k];
 #pragma unroll
         for (int k = 0; k < Cd; ++k) mu2[k] = rec[3 + k];
-        const float o_in = activated ? rec[D + 3] : sigmoid_f(rec[D + 3]);
-        const float beta0 = activated ? rec[D + 4] : beta_act_f(rec[D + 4]);
+        const float o_in = activated ? rec[D + 3] : sigmoid_fast(rec[D + 3]);
+        const float beta0 = activated ? rec[D + 4] : beta_act_fast(rec[D + 4]);
 #pragma unroll
-        for (int k = 0; k < Cd; ++k) beta_c[k] = activated ? rec[D + 5 + k] : beta_act_f(rec[D + 5 + k]);
+        for (int k = 0; k < Cd; ++k) beta_c[k] = activated ? rec[D + 5 + k] : beta_act_fast(rec[D + 5 + k]);
 #pragma unroll
-        for (int k = 0; k < D; ++k) s[k] = activated ? rec[2 * D + 2 + k] : softplus_f(rec[2 * D + 2 + k]);
+        for (int k = 0; k < D; ++k) s[k] = activated ? rec[2 * D + 2 + k] : softplus_fast(rec[2 * D + 2 + k]);
 #pragma unroll
         for (int k = 0; k < M; ++k) lt[k] = rec[3 * D + 2 + k];
         const float R[9] = {1.f, lt[0], lt[1], -lt[0], 1.f, lt[2], -lt[1], -lt[2], 1.f};
@@ -515,7 +519,7 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             const float raw = rec[2 * D + 2 + k];
-            grad[2 * D + 2 + k] = activated ? vs[k] : vs[k] * (raw > 20.f ? 1.f : sigmoid_f(raw));  // softplus'
+            grad[2 * D + 2 + k] = activated ? vs[k] : vs[k] * (raw > 20.f ? 1.f : sigmoid_fast(raw));  // softplus'
         }
 #pragma unroll
         for (int k = 0; k < M; ++k) grad[3 * D + 2 + k] = vlt[k];
@@ -622,9 +626,12 @@ extern "C" int ubs_fused_project_fwd(int C, int64_t N, int D, const float *recor
         if (n_isects != nullptr) UBS_CUDA_TRY(cudaMemsetAsync(n_isects, 0, sizeof(int64_t), s));
         return UBS_OK;
     }
-    UBS_CHECK_ARG(records && viewmats && Ks && (cam_pos || query) && radii && means2d && depths && conics && opacities &&
-                      betas && tiles_per_gauss && (workspace || tile_delta),
+    UBS_CHECK_ARG(records && viewmats && Ks && (cam_pos || query) && radii && means2d && depths &&
+                      (workspace || tile_delta),
                   "fused_project_fwd: null pointer");
+    UBS_CHECK_ARG((conics && opacities && betas && tiles_per_gauss) || (!conics && splats && tile_delta),
+                  "fused_project_fwd: conics / opacities / betas / tiles_per_gauss go together; a render-only frame "
+                  "(conics == NULL) needs the splat rows and the tile-binning route");
     UBS_CHECK_ARG(D != 7 || timestamps != nullptr || query != nullptr, "fused_project_fwd: D=7 needs timestamps");
     UBS_CHECK_ARG(((uintptr_t)records & 15) == 0, "fused_project_fwd: records must be 16-byte aligned");
     UBS_CHECK_ARG(CN < ((int64_t)1 << 31), "fused_project_fwd: C*N must fit int32 flatten ids");
