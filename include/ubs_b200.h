@@ -219,6 +219,19 @@ int ubs_rasterize_bwd_splats(int C, int64_t N, const int64_t *n_isects, int64_t 
                              const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
                              float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, float *v_betas,
                              float *v_depths, void *stream);
+/* RGB compositing backward of the fused path: colours from the splat rows, all screen-space gradients of a primitive
+ * accumulated (vector reductions) into ONE 48-byte row, v_rows [C,N,12], zeroed by the caller:
+ *   0..2  v_colors            3, 4, 5  v_conics = (r3, 2 r4, r5)
+ *   6, 7  moment form of v_means2d = (2a r6 + 2b r7, 2b r6 + 2c r7) with the primitive's conic (a, b, c)
+ *   8     v_opacities         9  v_betas / ln 2        10  v_depths (not written here)        11  unused
+ * ubs_fused_project_bwd* take these rows as `v_rows` (two sectors per visible primitive instead of eight).
+ * Same results as ubs_rasterize_bwd_splats(channels = 3) up to the order of the float additions
+ * (replaces rasterize_to_pixels_bwd.cu:106-274 for the (16-tile, 3-channel) instantiation).                     */
+int ubs_rasterize_bwd_rows(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity, const float *splats,
+                           const float *backgrounds, const uint8_t *masks, int width, int height, int tile_size,
+                           const int32_t *offsets, const int32_t *flatten_ids, const float *render_alphas,
+                           const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
+                           float *v_rows, void *stream);
 int ubs_rasterize_count(int C, const int64_t *n_isects, int64_t isect_capacity, const float *means2d,
                         const float *conics, const float *opacities, const float *betas, int width, int height,
                         int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
@@ -281,7 +294,9 @@ int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const f
                           int calc_compensations, const int32_t *radii, const float *conics,
                           const float *v_means2d, const float *v_depths, const float *v_conics,
                           const float *v_opacities, const float *v_betas, const float *v_colors, /* [C,N,3] or NULL */
-                          float *v_records,                                                       /* [N, stride] */
+                          const float *v_rows, /* NULL, or [C,N,12] rows of ubs_rasterize_bwd_rows: then read INSTEAD
+                                                  of the six v_* arrays (which may be NULL) */
+                          float *v_records,    /* [N, stride] */
                           int activated, const float *query, /* as in ubs_fused_project_fwd */
                           const int32_t *skip_flag, /* NULL, or the `status` of the frame's tile-list build: when
                                                        status[0] != 0 (the frame lost pairs to the capacity bound) the
@@ -328,8 +343,9 @@ int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *records, const fl
                                const float *cam_pos, const float *timestamps, int width, int height, float eps2d,
                                int calc_compensations, const int32_t *radii, const float *conics,
                                const float *v_means2d, const float *v_depths, const float *v_conics,
-                               const float *v_opacities, const float *v_betas, const float *v_colors, float *exp_avg,
-                               float *exp_avg_sq, const double *h_lr, double beta1, double beta2, double eps,
+                               const float *v_opacities, const float *v_betas, const float *v_colors,
+                               const float *v_rows, /* as in ubs_fused_project_bwd */
+                               float *exp_avg, float *exp_avg_sq, const double *h_lr, double beta1, double beta2, double eps,
                                int64_t step, double opacity_reg, double scale_reg,
                                const int32_t *skip_flag, /* as above; a truncated frame leaves records and moments
                                                             untouched */
@@ -349,8 +365,9 @@ int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *records, const 
                                   const float *cam_pos, const float *timestamps, int width, int height, float eps2d,
                                   int calc_compensations, const int32_t *radii, const float *conics,
                                   const float *v_means2d, const float *v_depths, const float *v_conics,
-                                  const float *v_opacities, const float *v_betas, const float *v_colors, int world,
-                                  int rank, int64_t shard_rows, float *const *h_staging,
+                                  const float *v_opacities, const float *v_betas, const float *v_colors,
+                                  const float *v_rows, /* as in ubs_fused_project_bwd */
+                                  int world, int rank, int64_t shard_rows, float *const *h_staging,
                                   const int32_t *skip_flag, /* as in ubs_fused_project_bwd: zero tiles are sent */
                                   void *stream);
 int ubs_reduce_adam_gather(int64_t N, int D, int world, int rank, int64_t shard_rows, const float *staging,

@@ -1,5 +1,7 @@
 """GPU parity of the fused fast path (packed records -> image) against the reference kernel chain
 K1 -> K2 -> K3 -> K5 -> K7-K9 -> K10 driven exactly as scene/beta_model.py:660-711 drives it."""
+import math
+
 import pytest
 import torch
 
@@ -239,6 +241,59 @@ def test_splat_rows_equal_the_separate_arrays_and_both_compositing_entries_agree
                                        W, H, 16, ptr(rz.offsets), ptr(rz.flatten_ids), ptr(rc3), ptr(ra3), ptr(last3), s),
           "fwd_splats")
     assert torch.equal(rc3, rc) and torch.equal(ra3, ra) and torch.equal(last3, rz.last_ids)
+
+
+@pytest.mark.parametrize("D,N,W,H,C,aa", [(6, 70000, 400, 304, 1, False), (7, 40000, 333, 250, 2, True),
+                                           (6, 3000, 1280, 720, 1, False)])
+def test_gradient_rows_equal_the_separate_gradient_arrays(D, N, W, H, C, aa):
+    """ubs_rasterize_bwd_rows (lane = pair, 4x4 blocks, vector reductions into one 48-byte row per primitive) against
+    ubs_rasterize_bwd_splats (separate arrays): the rows, decoded as include/ubs_b200.h documents, equal the arrays up
+    to the order of the float additions; and the projection backward gives the same parameter gradients from either
+    (FusedRasterizer(grad_rows=True / False)).  The last case has a few huge splats per tile (long single-pair runs,
+    short buckets), the second one partially covered border tiles, two cameras and the antialiased opacities."""
+    from ubs_b200 import fused, synth
+    from ubs_b200._lib import check, ptr
+
+    scene = synth.make_scene(N, D, seed=17 + D).to("cuda")
+    if N < 10000:
+        scene.scale.data += 1.5  # large splats: long lists of pairs that cover whole tiles
+    cams = synth.make_cameras(C, W, H, seed=6, timestamps=[0.3, 0.8][:C], device="cuda")
+    vm, K, cp = (torch.stack([getattr(c, k) for c in cams]) for k in ("viewmat", "K", "cam_pos"))
+    ts = torch.tensor([c.timestamp for c in cams], device="cuda") if D == 7 else None
+    bg = torch.rand(C, 3, device="cuda")
+    rec = fused.pack_records(D, *scene.tensors())
+    g = torch.Generator(device="cuda").manual_seed(3)
+    v_rc = torch.randn(C, H, W, 3, device="cuda", generator=g) / (H * W)
+    v_ra = torch.randn(C, H, W, 1, device="cuda", generator=g) / (H * W)
+    out = {}
+    for rows in (True, False):
+        rz = fused.FusedRasterizer(D, N, W, H, n_cams=C, antialiased=aa, grad_rows=rows, capacity=6_000_000)
+        rz.forward(rec, vm, K, cp, ts, bg)
+        assert not rz.overflowed()
+        out[rows] = (rz, rz.backward(rec, vm, K, cp, ts, bg, v_rc, v_ra))
+    (rz_r, g_r), (rz_a, g_a) = out[True], out[False]
+    assert int((rz_a.radii > 0).sum()) > min(N, 1000) // 2
+    r = rz_r.v_rows
+    a, b, c = rz_a.conics.unbind(-1)
+    decoded = {
+        "v_colors": (r[..., 0:3], rz_a.v_colors),
+        "v_conics": (torch.stack((r[..., 3], 2 * r[..., 4], r[..., 5]), -1), rz_a.v_conics),
+        "v_means2d": (torch.stack((2 * a * r[..., 6] + 2 * b * r[..., 7], 2 * b * r[..., 6] + 2 * c * r[..., 7]), -1),
+                      rz_a.v_means2d),
+        "v_opacities": (r[..., 8], rz_a.v_opacities),
+        "v_betas": (r[..., 9] * math.log(2.0), rz_a.v_betas),
+    }
+    vis = rz_a.radii > 0
+    for name, (x, y) in decoded.items():
+        x, y = x[vis].double(), y[vis].double()
+        scale = y.abs().max().item()
+        assert scale > 0, name
+        # sums of up to thousands of float terms in a different order (and a different factoring for v_means2d)
+        assert (x - y).abs().max().item() <= 2e-5 * scale, (name, (x - y).abs().max().item(), scale)
+        assert ((x - y).abs().sum() / y.abs().sum()).item() < 2e-6, name
+    assert (r[..., 10:] == 0).all() and (r[~vis] == 0).all()
+    scale = g_a.abs().amax(dim=0).clamp_min(1e-20)
+    assert ((g_r - g_a).abs().amax(dim=0) / scale).max().item() < 2e-4
 
 
 def test_render_only_frames_render_queue_and_host_pipeline_match_plain_forward():

@@ -328,8 +328,7 @@ def test_fused_projection_backward_adam_is_bit_identical_to_backward_then_adam(D
         cols = (ctypes.c_double * adam_b.stride)(*adam_b.lr_columns())
         check(rz.lib.ubs_fused_project_bwd_adam(
             1, N, D, ptr(rec_b), ptr(args[0]), ptr(args[1]), ptr(args[2]), ptr(ts), W, H, rz.eps2d, 0, ptr(rz.radii),
-            ptr(rz.conics), ptr(rz.v_means2d), None, ptr(rz.v_conics), ptr(rz.v_opacities), ptr(rz.v_betas),
-            ptr(rz.v_colors), ptr(adam_b.exp_avg), ptr(adam_b.exp_avg_sq), ctypes.cast(cols, ctypes.c_void_p), 0.9,
+            ptr(rz.conics), *rz.grad_args(), ptr(adam_b.exp_avg), ptr(adam_b.exp_avg_sq), ctypes.cast(cols, ctypes.c_void_p), 0.9,
             0.999, 1e-15, adam_b.step_count, 0.01, 0.02, ptr(rz.status), s), "ubs_fused_project_bwd_adam")
         assert torch.equal(rec_a, rec_b), it
         assert torch.equal(adam_a.exp_avg, adam_b.exp_avg) and torch.equal(adam_a.exp_avg_sq, adam_b.exp_avg_sq), it

@@ -265,6 +265,7 @@ struct BwdOpts {
     int activated;             // records hold activated values (see decode_record): no activation derivative
     const float *query;        // NULL, or [N, D-3] queries given by the caller instead of the view direction
     const int32_t *skip_flag;  // NULL, or the `status` word of the frame's tile-list build
+    const float *v_rows;       // NULL, or the 48-byte gradient rows of ubs_rasterize_bwd_rows (then instead of v_*)
 };
 
 // Backward of fused_project_fwd_kernel: one thread per primitive, looping over cameras, so the per-primitive sums
@@ -337,16 +338,21 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
                 const int64_t idx = (int64_t)(cid - 1) * N + base + threadIdx.x;
                 prefetch_l1(conics + idx * 3);
                 prefetch_l1(conics + idx * 3 + 2);
-                prefetch_l1(v_means2d + idx * 2);
-                prefetch_l1(v_conics + idx * 3);
-                prefetch_l1(v_conics + idx * 3 + 2);
-                prefetch_l1(v_opacities + idx);
-                prefetch_l1(v_betas + idx);
-                if (v_colors != nullptr) {
-                    prefetch_l1(v_colors + idx * 3);
-                    prefetch_l1(v_colors + idx * 3 + 2);
+                if (opts.v_rows != nullptr) {  // one 48-byte row: two sectors
+                    prefetch_l1(opts.v_rows + idx * 12);
+                    prefetch_l1(opts.v_rows + idx * 12 + 8);
+                } else {
+                    prefetch_l1(v_means2d + idx * 2);
+                    prefetch_l1(v_conics + idx * 3);
+                    prefetch_l1(v_conics + idx * 3 + 2);
+                    prefetch_l1(v_opacities + idx);
+                    prefetch_l1(v_betas + idx);
+                    if (v_colors != nullptr) {
+                        prefetch_l1(v_colors + idx * 3);
+                        prefetch_l1(v_colors + idx * 3 + 2);
+                    }
+                    if (v_depths != nullptr) prefetch_l1(v_depths + idx);
                 }
-                if (v_depths != nullptr) prefetch_l1(v_depths + idx);
             }
         }
         const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -455,9 +461,28 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
             cond_apply<Cd>(prep, xyz, x, o_in, beta_c, mean, o_cond);
 
             const float conic[3] = {conics[idx * 3], conics[idx * 3 + 1], conics[idx * 3 + 2]};
-            const float vm[2] = {v_means2d[idx * 2], v_means2d[idx * 2 + 1]};
-            const float vc[3] = {v_conics[idx * 3], v_conics[idx * 3 + 1], v_conics[idx * 3 + 2]};
-            float v_o = v_opacities[idx];
+            float vm[2], vc[3], v_o, v_b, v_d, v_col[3];
+            if (opts.v_rows != nullptr) {  // layout: include/ubs_b200.h, ubs_rasterize_bwd_rows
+                const float4 *row = reinterpret_cast<const float4 *>(opts.v_rows + idx * 12);
+                const float4 q0 = row[0], q1 = row[1], q2 = row[2];
+                v_col[0] = q0.x, v_col[1] = q0.y, v_col[2] = q0.z;
+                vc[0] = q0.w, vc[1] = q1.x + q1.x, vc[2] = q1.y;
+                const float a2 = conic[0] + conic[0], b2 = conic[1] + conic[1], c2 = conic[2] + conic[2];
+                vm[0] = __fmaf_rn(a2, q1.z, b2 * q1.w);
+                vm[1] = __fmaf_rn(b2, q1.z, c2 * q1.w);
+                v_o = q2.x, v_b = q2.y * 0.693147180559945f, v_d = q2.z;
+            } else {
+                vm[0] = v_means2d[idx * 2], vm[1] = v_means2d[idx * 2 + 1];
+                vc[0] = v_conics[idx * 3], vc[1] = v_conics[idx * 3 + 1], vc[2] = v_conics[idx * 3 + 2];
+                v_o = v_opacities[idx], v_b = v_betas[idx];
+                v_d = v_depths != nullptr ? v_depths[idx] : 0.f;
+                if (v_colors != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) v_col[k] = v_colors[idx * 3 + k];
+                } else {
+                    v_col[0] = v_col[1] = v_col[2] = 0.f;
+                }
+            }
             float comp = 0.f, v_comp = 0.f;
             if (calc_comp) {
                 const Splat2D f = project_splat(cam, mean, s6, width, height, eps2d, -3.0e38f, 3.0e38f, -1.f);
@@ -466,9 +491,8 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
                 v_o = v_o * comp;
             }
             float v_mean[3] = {0.f, 0.f, 0.f}, v_s6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            project_splat_vjp(cam, mean, s6, width, height, eps2d, conic, calc_comp ? &comp : nullptr, vm,
-                              v_depths != nullptr ? v_depths[idx] : 0.f, vc, calc_comp ? &v_comp : nullptr, v_mean,
-                              v_s6, nullptr, nullptr);
+            project_splat_vjp(cam, mean, s6, width, height, eps2d, conic, calc_comp ? &comp : nullptr, vm, v_d, vc,
+                              calc_comp ? &v_comp : nullptr, v_mean, v_s6, nullptr, nullptr);
             // index-backward of the 3x3 -> 6 gather: only the upper triangle receives gradient (rendering.py:55-56)
             const float gV[9] = {v_s6[0], v_s6[1], v_s6[2], 0.f, v_s6[3], v_s6[4], 0.f, 0.f, v_s6[5]};
             float g_mu1[3], g_mu2[Cd], g11[9], g12[3 * Cd], g21[Cd * 3], g22[Cd * Cd], go, gb[Cd];
@@ -481,11 +505,9 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
                 g_beta_c[k] += gb[k];
             }
             g_o += go;
-            g_beta0 += v_betas[idx];
-            if (v_colors != nullptr) {
+            g_beta0 += v_b;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) g_rgb[k] += v_colors[idx * 3 + k];
-            }
+            for (int k = 0; k < 3; ++k) g_rgb[k] += v_col[k];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -666,14 +688,14 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
                                      int height, float eps2d, int calc_compensations, const int32_t *radii,
                                      const float *conics, const float *v_means2d, const float *v_depths,
                                      const float *v_conics, const float *v_opacities, const float *v_betas,
-                                     const float *v_colors, float *v_records, int activated, const float *query,
+                                     const float *v_colors, const float *v_rows, float *v_records, int activated, const float *query,
                                      const int32_t *skip_flag, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "fused_project_bwd: bad sizes");
     UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd: D must be 6 or 7 (got %d)", D);
     if (N == 0) return UBS_OK;
-    UBS_CHECK_ARG(records && viewmats && Ks && (cam_pos || query) && radii && conics && v_means2d && v_conics &&
-                      v_opacities && v_betas && v_records,
+    UBS_CHECK_ARG(records && viewmats && Ks && (cam_pos || query) && radii && conics &&
+                      (v_rows || (v_means2d && v_conics && v_opacities && v_betas)) && v_records,
                   "fused_project_bwd: null pointer");
     UBS_CHECK_ARG(D != 7 || timestamps != nullptr || query != nullptr, "fused_project_bwd: D=7 needs timestamps");
     UBS_CHECK_ARG((((uintptr_t)records | (uintptr_t)v_records) & 15) == 0,
@@ -685,7 +707,7 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
     const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams unused{};
     const ScatterDst no_scatter{};
-    const BwdOpts opts{activated, query, skip_flag};
+    const BwdOpts opts{activated, query, skip_flag, v_rows};
     if (D == 6)
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
@@ -705,15 +727,15 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
                                           int height, float eps2d, int calc_compensations, const int32_t *radii,
                                           const float *conics, const float *v_means2d, const float *v_depths,
                                           const float *v_conics, const float *v_opacities, const float *v_betas,
-                                          const float *v_colors, float *exp_avg, float *exp_avg_sq, const double *h_lr,
+                                          const float *v_colors, const float *v_rows, float *exp_avg, float *exp_avg_sq, const double *h_lr,
                                           double beta1, double beta2, double eps, int64_t step, double opacity_reg,
                                           double scale_reg, const int32_t *skip_flag, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "fused_project_bwd_adam: bad sizes");
     UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd_adam: D must be 6 or 7 (got %d)", D);
     if (N == 0) return UBS_OK;
-    UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && conics && v_means2d && v_conics && v_opacities &&
-                      v_betas && exp_avg && exp_avg_sq && h_lr,
+    UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && conics &&
+                      (v_rows || (v_means2d && v_conics && v_opacities && v_betas)) && exp_avg && exp_avg_sq && h_lr,
                   "fused_project_bwd_adam: null pointer");
     UBS_CHECK_ARG(D != 7 || timestamps != nullptr, "fused_project_bwd_adam: D=7 needs timestamps");
     UBS_CHECK_ARG(step >= 1, "fused_project_bwd_adam: step counts from 1 (got %lld)", (long long)step);
@@ -723,7 +745,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
     const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
     const size_t smem = (size_t)3 * kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
-    const BwdOpts opts{0, nullptr, skip_flag};
+    const BwdOpts opts{0, nullptr, skip_flag, v_rows};
     if (D == 6) {
         UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<6, 3, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -752,7 +774,7 @@ extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *reco
                                              int width, int height, float eps2d, int calc_compensations,
                                              const int32_t *radii, const float *conics, const float *v_means2d,
                                              const float *v_depths, const float *v_conics, const float *v_opacities,
-                                             const float *v_betas, const float *v_colors, int world, int rank,
+                                             const float *v_betas, const float *v_colors, const float *v_rows, int world, int rank,
                                              int64_t shard_rows, float *const *h_staging, const int32_t *skip_flag,
                                              void *stream) {
     using namespace ubs;
@@ -763,8 +785,8 @@ extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *reco
     UBS_CHECK_ARG(shard_rows > 0 && shard_rows % kFusedThreads == 0 && shard_rows * world >= N,
                   "fused_project_bwd_scatter: shard_rows must be a positive multiple of %d covering N", kFusedThreads);
     if (N == 0) return UBS_OK;
-    UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && conics && v_means2d && v_conics && v_opacities &&
-                      v_betas && h_staging,
+    UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && conics &&
+                      (v_rows || (v_means2d && v_conics && v_opacities && v_betas)) && h_staging,
                   "fused_project_bwd_scatter: null pointer");
     UBS_CHECK_ARG(D != 7 || timestamps != nullptr, "fused_project_bwd_scatter: D=7 needs timestamps");
     ScatterDst sc{};
@@ -779,7 +801,7 @@ extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *reco
     const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
     const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams unused{};
-    const BwdOpts opts{0, nullptr, skip_flag};
+    const BwdOpts opts{0, nullptr, skip_flag, v_rows};
     if (D == 6)
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             1, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,

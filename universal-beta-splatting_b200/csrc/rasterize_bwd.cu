@@ -9,6 +9,8 @@
 //      butterfly, after which lane l holds the warp total of component l;
 //   3. 30 lanes add those totals into a shared-memory accumulator [pair][component] in one instruction;
 //   4. after the batch, each thread flushes one pair with at most 10 global atomics -- one set per (tile, pair).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "raster_common.cuh"
 
@@ -520,6 +522,411 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
     }
 }
 
+
+// ---- RGB path, lane = pair ("pair-lane") ---------------------------------------------------------------------------
+// Same results as rasterize_bwd3_kernel, with the roles of lanes and loop swapped inside every (pixels x pairs) block of
+// work.  There: lane = pixel, loop over the pairs of the warp's culled list, the per-pair sums over pixels need a
+// transposing butterfly (31 SHFL + 62 SEL + 31 FADD per three pairs) and the sub-tile a warp culls against is tied to
+// the warp width (8x4 pixels).  Here: lane = pair (its 48-byte record and its ten sums live in registers for a whole
+// bucket of up to 32 pairs), the loop runs over the pixels of a 4x4 block, and what has to cross lanes is the
+// per-pixel sequential state instead: walking a pixel's pairs back to front is the composition of the affine maps
+//     (T, B) -> (ra T,  B + alpha ra cv T),     ra = 1 / (1 - alpha),  cv = colour . v_render_colour,
+// so one inclusive warp scan over the monoid  (R1, K1) o (R2, K2) = (R1 R2, K1 + K2 R1)  -- five stages of two SHFL,
+// one FMUL, one FFMA -- gives every lane the transmittance in front of its pair and the colour behind it
+// (rasterize_to_pixels_bwd.cu:190-214 keeps both sequentially).  Nothing is reduced across lanes, the per-pixel state
+// (T, B) sits in shared memory between buckets, and the cull granularity is free of the warp width: 4x4 blocks leave
+// ~20 % fewer evaluations than 8x4 sub-tiles.  A bucket of <= 16 (<= 8) pairs runs two (four) pixels per step in
+// 16-lane (8-lane) segments so that short lists do not idle lanes.
+constexpr int kBlk = 4;                     // block edge in pixels
+constexpr int kBlkPix = kBlk * kBlk;        // 16 pixels per block, 16 blocks per tile: bit (by * 4 + bx) of a pair's mask
+
+// Which 4x4 blocks of the tile can {sigma < 1} of a conic (a, b, c) centred at (mx, my) touch.  Exact up to the stated
+// margins: for each of the four block rows, the x-extent of the ellipse restricted to the rows' y-slab (the right edge
+// x = (-b v + sqrt(a - det v^2)) / a is concave in v = y - my with its maximum at v* = -b / sqrt(det c); the left edge
+// mirrors it), compared with the four block columns.  (tx0, ty0) = centre of the tile's first pixel.
+__device__ __forceinline__ uint32_t block_mask16(float mx, float my, float a, float b, float c, float tx0, float ty0) {
+    const float det = a * c - b * b;
+    if (!(det > 0.f && a > 0.f && c > 0.f)) return 0xFFFFu;  // degenerate conic: never culled
+    const float hy = sqrtf(a / det);
+    const float vstar = -b * rsqrtf(det * c);
+    const float ra = 1.f / a;
+    const float u0 = tx0 - mx;  // first pixel column relative to the centre
+    uint32_t mask = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float d0 = ty0 + (float)(kBlk * r) - my;
+        const float lo = fmaxf(d0 - 0.01f, -hy), hi = fminf(d0 + (float)(kBlk - 1) + 0.01f, hy);
+        if (lo > hi) continue;
+        const float vr = fminf(fmaxf(vstar, lo), hi), vl = fminf(fmaxf(-vstar, lo), hi);
+        float xr = (sqrtf(fmaxf(0.f, a - det * vr * vr)) - b * vr) * ra;
+        float xl = (-sqrtf(fmaxf(0.f, a - det * vl * vl)) - b * vl) * ra;
+        xr += 0.01f + 0.001f * fabsf(xr);
+        xl -= 0.01f + 0.001f * fabsf(xl);
+        uint32_t cols = 0;
+#pragma unroll
+        for (int cx = 0; cx < 4; ++cx)
+            if (xl <= u0 + (float)(kBlk * cx + kBlk - 1) && xr >= u0 + (float)(kBlk * cx)) cols |= 1u << cx;
+        mask |= cols << (4 * r);
+    }
+    return mask;
+}
+
+// shfl.sync.up inside W-lane segments as a volatile asm statement: the compiler keeps volatile statements in source order,
+// which is what interleaves the scans of independent pixels (left alone it finishes one scan before starting the next)
+template <int W>
+__device__ __forceinline__ float shfl_up_ordered(float v, int off) {
+    float r;
+    asm volatile("shfl.sync.up.b32 %0, %1, %2, %3, 0xffffffff;" : "=f"(r) : "f"(v), "r"(off), "r"((32 - W) << 8));
+    return r;
+}
+
+// red.global.add.v4.f32 / .v2.f32 (sm_90+): one fire-and-forget reduction per 16 / 8 bytes
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float *p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// One bucket: lanes j = lane % W hold the pairs list[0 .. n), n <= W; 32 / W pixels of the block are processed per step and
+// NCH steps (independent pixels) are advanced together: the shuffles of their scans are issued stage by stage for all of
+// them, so that one chain's SHFL latency is covered by the others (the compiler keeps shuffles in source order).
+template <int W, int NCH, bool ROWS_OUT>
+__device__ __forceinline__ void pairlane_bucket(uint32_t lane, const uint8_t *__restrict__ list, int32_t n,
+                                                const Staged3 *__restrict__ s_rec, float *__restrict__ s_acc,
+                                                const int32_t *__restrict__ s_id, float *__restrict__ v_rows,
+                                                const float4 *__restrict__ pix_const, float4 *__restrict__ pix_state,
+                                                float pxb, float pyb, int32_t batch_end) {
+    constexpr int G = 32 / W;                  // pixels per step
+    constexpr int STEPS = kBlkPix / G;         // steps per block (W = 32: 16, 16: 8, 8: 4)
+    constexpr int XS = kBlk / G;               // steps per pixel row (W = 32: 4, 16: 2, 8: 1)
+    static_assert(STEPS % NCH == 0, "chains per iteration must divide the steps of a block");
+    const uint32_t j = lane & (W - 1), ph = lane / W;
+    const bool has = (int32_t)j < n;
+    const uint32_t slot = has ? (uint32_t)list[j] : (uint32_t)kTilePixels;  // [kTilePixels] = the NaN sentinel
+    const float4 xyob = s_rec[slot].xyob, conic = s_rec[slot].conic, col = s_rec[slot].col;
+    const int32_t pair_idx = batch_end - (int32_t)slot;  // position of the pair in the sorted list
+    float acc[kGrad3];
+#pragma unroll
+    for (int k = 0; k < kGrad3; ++k) acc[k] = 0.f;
+    const float px0 = pxb + (float)ph;  // G > 1: the lane's pixel column inside a step
+    const float4 *pc_it = pix_const + ph;
+    float4 *ps_it = pix_state + ph;
+    float py0 = pyb, px_it = px0;  // px_it: first column of the iteration when a pixel row takes several iterations
+    constexpr int ROWS = NCH >= XS ? NCH / XS : 1;  // pixel rows per iteration
+#pragma unroll 1
+    for (int it = 0; it < STEPS / NCH; ++it) {
+        float4 pc[NCH];
+        float T0[NCH], B0[NCH], dx[NCH], dy[NCH], alpha[NCH], ra[NCH], cv[NCH], lg[NCH], vis_g[NCH], w_g[NCH], ov_g[NCH];
+        float R[NCH], K[NCH];
+#pragma unroll
+        for (int t = 0; t < NCH; ++t) {
+            // step s = it * NCH + t covers pixel s * G + ph of the block: column (s % XS) * G + ph, row s / XS
+            const int xs = NCH >= XS ? t % XS : -1, row = NCH >= XS ? t / XS : 0;
+            const int pix = NCH >= XS ? row * kBlk + xs * G : t * G;  // offset from pc_it (NCH < XS: part of one row)
+            pc[t] = pc_it[pix];  // v_r, v_g, v_b, Kc
+            const float4 ps = ps_it[pix];  // T, B, last_ids
+            T0[t] = ps.x, B0[t] = ps.y;
+            const float px = (NCH >= XS ? px0 : px_it) + (float)((NCH >= XS ? xs : t) * G);
+            const float py = py0 + (float)row;
+            dx[t] = xyob.x - px, dy[t] = xyob.y - py;
+            const float sigma = __fmaf_rn(dy[t], dx[t] * conic.y, __fmaf_rn(dx[t], conic.x * dx[t], dy[t] * (conic.z * dy[t])));
+            // sigma in [0, 1) and the pair not behind this pixel's last contributor (rasterize_to_pixels_bwd.cu:166-168)
+            const bool valid = (__float_as_uint(sigma) < 0x3f800000u) && (pair_idx <= __float_as_int(ps.z));
+            const float om = 1.f - (valid ? sigma : 0.f);
+            lg[t] = __log2f(om);
+            const float vis = valid ? exp2f(xyob.w * lg[t]) : 0.f;
+            const float ov = xyob.z * vis;
+            alpha[t] = fminf(0.999f, ov);
+            ra[t] = fast_rcp(1.f - alpha[t]);
+            cv[t] = __fmaf_rn(col.z, pc[t].z, __fmaf_rn(col.y, pc[t].y, col.x * pc[t].x));
+            const bool live = ov <= 0.999f;  // the clamp has zero slope above it (rasterize_to_pixels_bwd.cu:230)
+            ov_g[t] = live ? ov : 0.f;
+            vis_g[t] = live ? vis : 0.f;
+            w_g[t] = ov_g[t] * fast_rcp(om);  // o beta (1-sigma)^(beta-1) = beta ov / (1-sigma)
+            R[t] = ra[t], K[t] = (alpha[t] * ra[t]) * cv[t];
+        }
+        // inclusive scans of (R, K) over the pairs of the bucket, furthest back first; all chains stage by stage
+#pragma unroll
+        for (int off = 1; off < W; off <<= 1) {
+            float Rp[NCH], Kp[NCH];
+#pragma unroll
+            for (int t = 0; t < NCH; ++t) {
+                Rp[t] = shfl_up_ordered<W>(R[t], off);
+                Kp[t] = shfl_up_ordered<W>(K[t], off);
+            }
+            if ((int)j >= off) {
+#pragma unroll
+                for (int t = 0; t < NCH; ++t) {
+                    K[t] = __fmaf_rn(K[t], Rp[t], Kp[t]);
+                    R[t] *= Rp[t];
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NCH; ++t) {
+            const int xs = NCH >= XS ? t % XS : -1, row = NCH >= XS ? t / XS : 0;
+            const int pix = NCH >= XS ? row * kBlk + xs * G : t * G;
+            const float Tl = T0[t] * R[t];                      // transmittance in front of this pair
+            const float fac = alpha[t] * Tl;
+            const float B_after = __fmaf_rn(T0[t], K[t], B0[t]);   // sum_k buffer[k] v_rc[k] including this pair
+            const float B_before = __fmaf_rn(-fac, cv[t], B_after);
+            if (j == W - 1) *reinterpret_cast<float2 *>(ps_it + pix) = make_float2(Tl, B_after);
+            const float v_alpha = __fmaf_rn(Tl, cv[t], ra[t] * (pc[t].w - B_before));
+            acc[0] = __fmaf_rn(fac, pc[t].x, acc[0]);
+            acc[1] = __fmaf_rn(fac, pc[t].y, acc[1]);
+            acc[2] = __fmaf_rn(fac, pc[t].z, acc[2]);
+            const float v_sigma = -(v_alpha * xyob.w) * w_g[t];
+            const float tx = dx[t] * v_sigma, ty = dy[t] * v_sigma;
+            acc[3] = __fmaf_rn(tx, dx[t], acc[3]);
+            acc[4] = __fmaf_rn(tx, dy[t], acc[4]);
+            acc[5] = __fmaf_rn(ty, dy[t], acc[5]);
+            acc[6] += tx;
+            acc[7] += ty;
+            acc[8] = __fmaf_rn(vis_g[t], v_alpha, acc[8]);
+            acc[9] = __fmaf_rn(v_alpha * ov_g[t], lg[t], acc[9]);
+        }
+        if constexpr (NCH >= XS) {
+            py0 += (float)ROWS;
+            pc_it += ROWS * kBlk, ps_it += ROWS * kBlk;
+        } else {
+            if ((it + 1) % (XS / NCH) == 0) py0 += 1.f, px_it = px0;
+            else px_it += (float)(NCH * G);
+            pc_it += NCH * G, ps_it += NCH * G;
+        }
+    }
+    if constexpr (G > 1) {  // the segments hold the same pairs: add their sums
+#pragma unroll
+        for (int off = W; off < 32; off <<= 1) {
+#pragma unroll
+            for (int k = 0; k < kGrad3; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+        }
+    }
+    if (has && ph == 0) {
+        if constexpr (ROWS_OUT) {
+            // the ten sums of this (block, pair) go straight to the primitive's 48-byte gradient row: three vector
+            // reductions -- unless no pixel of the block was inside the support (every sum is then a signed zero)
+            uint32_t bits = 0;
+#pragma unroll
+            for (int k = 0; k < kGrad3; ++k) bits |= __float_as_uint(acc[k]);
+            if ((bits << 1) != 0u) {
+                float *row = v_rows + (size_t)s_id[slot] * kAccStride;
+                red_add_v4(row, acc[0], acc[1], acc[2], acc[3]);
+                red_add_v4(row + 4, acc[4], acc[5], acc[6], acc[7]);
+                red_add_v2(row + 8, acc[8], acc[9]);
+            }
+        } else {
+            float *row = s_acc + slot * kAccStride;
+#pragma unroll
+            for (int k = 0; k < kGrad3; ++k) atomicAdd(row + k, acc[k]);
+        }
+    }
+}
+
+template <int NCH, int MINB, bool ROWS_OUT>
+__global__ void __launch_bounds__(kTilePixels, MINB)
+rasterize_bwd3_pairlane_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev, int64_t isect_capacity,
+                               const float2 *__restrict__ means2d, const float *__restrict__ conics,
+                               const float *__restrict__ colors, const float *__restrict__ opacities,
+                               const float *__restrict__ betas, const float *__restrict__ backgrounds,
+                               const uint8_t *__restrict__ masks, uint32_t width, uint32_t height, uint32_t tile_width,
+                               uint32_t tile_height, const int32_t *__restrict__ tile_offsets,
+                               const int32_t *__restrict__ flatten_ids, const float *__restrict__ render_alphas,
+                               const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
+                               const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
+                               float *__restrict__ v_conics, float *__restrict__ v_colors,
+                               float *__restrict__ v_opacities, float *__restrict__ v_betas,
+                               const float4 *__restrict__ splats, bool splat_colors, float *__restrict__ v_rows) {
+    const uint32_t cam = blockIdx.z;
+    const uint32_t tile_id = blockIdx.y * tile_width + blockIdx.x;
+    const uint32_t tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
+    // pixels in block order: thread tr initialises pixel (tr & 15) of block (tr >> 4); warp w then owns blocks 2w, 2w + 1,
+    // i.e. exactly the pixels its own threads initialised (the state never crosses warps)
+    const uint32_t blk = tr >> 4, sp = tr & 15;
+    const uint32_t i = blockIdx.y * kTile + (blk >> 2) * kBlk + (sp >> 2);
+    const uint32_t j = blockIdx.x * kTile + (blk & 3) * kBlk + (sp & 3);
+    const bool inside = (i < height && j < width);
+
+    tile_offsets += (size_t)cam * tile_height * tile_width;
+    if (backgrounds != nullptr) backgrounds += cam * 3;
+    if (masks != nullptr && !masks[(size_t)cam * tile_height * tile_width + tile_id]) return;
+
+    const int64_t n_isects = min(*n_isects_dev, isect_capacity);
+    const int32_t range_start = tile_offsets[tile_id];
+    const int32_t range_end = (cam == (uint32_t)C - 1 && tile_id == tile_width * tile_height - 1)
+                                  ? (int32_t)n_isects
+                                  : tile_offsets[tile_id + 1];
+    const int32_t num_batches = (range_end - range_start + kTilePixels - 1) / kTilePixels;
+    if (num_batches <= 0) return;
+
+    __shared__ Staged3 s_rec[kTilePixels + 1];  // [kTilePixels] = sentinel (sigma = NaN) for lanes without a pair
+    __shared__ __align__(16) uint16_t s_mask[kTilePixels];  // blocks the support of each staged pair can touch (0 past the batch)
+    __shared__ int32_t s_id[kTilePixels];
+    __shared__ __align__(16) float s_acc[ROWS_OUT ? 4 : kTilePixels * kAccStride];
+    __shared__ float4 s_pix_const[kTilePixels];  // v_r, v_g, v_b, T_final (v_ra - bg . v_rc)
+    __shared__ float4 s_pix_state[kTilePixels];  // T, B = sum_k buffer[k] v_rc[k], last_ids
+    __shared__ uint8_t s_list[kTilePixels / 32][2][kTilePixels];
+
+    const float tx0 = (float)(blockIdx.x * kTile) + 0.5f, ty0 = (float)(blockIdx.y * kTile) + 0.5f;  // first pixel centre
+    const float kNaN = __int_as_float(0x7fffffff);
+    if (tr == 0) {
+        s_rec[kTilePixels].xyob = make_float4(kNaN, kNaN, 0.f, 1.f);
+        s_rec[kTilePixels].conic = make_float4(1.f, 0.f, 1.f, 0.f);
+        s_rec[kTilePixels].col = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // per-pixel state
+    int32_t bin_final = -1;
+    {
+        const size_t pix = inside ? ((size_t)cam * height + i) * width + j : 0;
+        const float T_final = inside ? 1.f - render_alphas[pix] : 1.f;
+        const float v_r = inside ? v_render_colors[pix * 3 + 0] : 0.f;
+        const float v_g = inside ? v_render_colors[pix * 3 + 1] : 0.f;
+        const float v_b = inside ? v_render_colors[pix * 3 + 2] : 0.f;
+        float Kc = inside ? v_render_alphas[pix] : 0.f;
+        if (backgrounds != nullptr) Kc -= backgrounds[0] * v_r + backgrounds[1] * v_g + backgrounds[2] * v_b;
+        Kc *= T_final;
+        if (inside) bin_final = last_ids[pix];
+        s_pix_const[tr] = make_float4(v_r, v_g, v_b, Kc);
+        s_pix_state[tr] = make_float4(T_final, 0.f, __int_as_float(bin_final), 0.f);
+    }
+    int32_t blk_bin_final = bin_final;  // furthest-front contributor of any pixel of the thread's block
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1)
+        blk_bin_final = max(blk_bin_final, __shfl_xor_sync(0xffffffffu, blk_bin_final, off));
+    const int32_t bin_final_a = __shfl_sync(0xffffffffu, blk_bin_final, 0);
+    const int32_t bin_final_b = __shfl_sync(0xffffffffu, blk_bin_final, 16);
+    const uint32_t bit_a = 2 * warp;  // mask bit of the warp's first block; the second is bit_a + 1
+    const float pxb_a = tx0 + (float)((bit_a & 3) * kBlk), pyb = ty0 + (float)((warp >> 1) * kBlk);
+
+    if constexpr (!ROWS_OUT)
+        for (int k = tr; k < kTilePixels * kAccStride; k += kTilePixels) s_acc[k] = 0.f;
+
+    for (int32_t b = 0; b < num_batches; ++b) {
+        __syncthreads();  // previous batch fully consumed and flushed
+        const int32_t batch_end = range_end - 1 - kTilePixels * b;  // pair index held by slot 0 (furthest back)
+        const int32_t batch_size = min((int32_t)kTilePixels, batch_end + 1 - range_start);
+        const int32_t idx = batch_end - (int32_t)tr;
+        if (idx >= range_start) {
+            const int32_t g = flatten_ids[idx];
+            s_id[tr] = g;
+            float4 xyob, col;
+            float ca, cb, cc;
+            if (splats != nullptr) {  // 48-byte rows of the fused projection kernel (see rasterize_fwd.cu)
+                xyob = splats[(size_t)g * 3];
+                const float4 cn = splats[(size_t)g * 3 + 1];
+                ca = cn.x, cb = cn.y, cc = cn.z;
+            } else {
+                const float2 xy = means2d[g];
+                xyob = make_float4(xy.x, xy.y, opacities[g], betas[g]);
+                ca = conics[(size_t)g * 3], cb = conics[(size_t)g * 3 + 1], cc = conics[(size_t)g * 3 + 2];
+            }
+            if (splats != nullptr && splat_colors) {
+                col = splats[(size_t)g * 3 + 2];
+                col.w = 0.f;
+            } else {
+                col = make_float4(colors[(size_t)g * 3], colors[(size_t)g * 3 + 1], colors[(size_t)g * 3 + 2], 0.f);
+            }
+            s_rec[tr].xyob = xyob;
+            s_rec[tr].conic = make_float4(ca, cb + cb, cc, 0.f);
+            s_rec[tr].col = col;
+            s_mask[tr] = (uint16_t)block_mask16(xyob.x, xyob.y, ca, cb, cc, tx0, ty0);
+        } else {
+            s_mask[tr] = 0;
+        }
+        __syncthreads();
+
+        // per-warp lists of the staged pairs that can touch block a / block b, in order.  Lane l takes the staged pairs
+        // 8 l .. 8 l + 7 (one 128-bit load of their masks); one warp scan of the packed per-lane counts places them.
+        // Slot p holds pair batch_end - p; pairs in front of every pixel's last contributor are left out.
+        uint32_t cnt_a, cnt_b;
+        {
+            const uint4 m4 = *reinterpret_cast<const uint4 *>(s_mask + 8 * lane);
+            const uint32_t w[4] = {m4.x >> bit_a, m4.y >> bit_a, m4.z >> bit_a, m4.w >> bit_a};
+            uint32_t hits_a = 0, hits_b = 0;  // bit k: staged pair 8 lane + k
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                hits_a |= ((w[q] & 1u) | ((w[q] >> 15) & 2u)) << (2 * q);
+                hits_b |= (((w[q] >> 1) & 1u) | ((w[q] >> 16) & 2u)) << (2 * q);
+            }
+            const int32_t skip_a = max(0, batch_end - bin_final_a) - 8 * (int32_t)lane;  // leading pairs to leave out
+            const int32_t skip_b = max(0, batch_end - bin_final_b) - 8 * (int32_t)lane;
+            hits_a = skip_a >= 8 ? 0u : (skip_a > 0 ? hits_a & (0xFFu << skip_a) : hits_a);
+            hits_b = skip_b >= 8 ? 0u : (skip_b > 0 ? hits_b & (0xFFu << skip_b) : hits_b);
+            const uint32_t mine = (uint32_t)__popc(hits_a) | ((uint32_t)__popc(hits_b) << 16);
+            uint32_t incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+                if ((int)lane >= off) incl += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            cnt_a = total & 0xFFFFu, cnt_b = total >> 16;
+            uint32_t pos_a = (incl - mine) & 0xFFFFu, pos_b = (incl - mine) >> 16;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if ((hits_a >> k) & 1u) s_list[warp][0][pos_a++] = (uint8_t)(8u * lane + (uint32_t)k);
+                if ((hits_b >> k) & 1u) s_list[warp][1][pos_b++] = (uint8_t)(8u * lane + (uint32_t)k);
+            }
+        }
+        __syncwarp();
+
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const uint8_t *list = s_list[warp][h];
+            const int32_t cnt = (int32_t)(h == 0 ? cnt_a : cnt_b);
+            const float4 *pc = s_pix_const + 32 * warp + kBlkPix * h;
+            float4 *ps = s_pix_state + 32 * warp + kBlkPix * h;
+            const float pxb = pxb_a + (float)(kBlk * h);
+#pragma unroll 1
+            for (int32_t base = 0; base < cnt; base += 32) {
+                const int32_t n = min(32, cnt - base);
+                if (n > 16) pairlane_bucket<32, NCH, ROWS_OUT>(lane, list + base, n, s_rec, s_acc, s_id, v_rows, pc, ps, pxb, pyb, batch_end);
+                else if (n > 8) pairlane_bucket<16, NCH, ROWS_OUT>(lane, list + base, n, s_rec, s_acc, s_id, v_rows, pc, ps, pxb, pyb, batch_end);
+                else pairlane_bucket<8, NCH, ROWS_OUT>(lane, list + base, n, s_rec, s_acc, s_id, v_rows, pc, ps, pxb, pyb, batch_end);
+                __syncwarp();  // the bucket's state writes are visible to the next bucket's reads
+            }
+        }
+        if constexpr (ROWS_OUT) continue;
+        __syncthreads();
+
+        // flush: one set of global atomics per (tile, pair); finish the moment form here
+        if ((int32_t)tr < batch_size) {
+            float4 *acc = reinterpret_cast<float4 *>(s_acc + tr * kAccStride);  // 48-byte rows: three vector loads
+            const float4 q0 = acc[0], q1 = acc[1], q2 = acc[2];
+            const float a[kGrad3] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
+            bool nz = false;
+#pragma unroll
+            for (int k = 0; k < kGrad3; ++k) nz |= (a[k] != 0.f);
+            if (nz) {
+                const size_t g = (size_t)s_id[tr];
+                const float4 conic = s_rec[tr].conic;  // a, 2b, c
+                atomicAdd(v_colors + g * 3 + 0, a[0]);
+                atomicAdd(v_colors + g * 3 + 1, a[1]);
+                atomicAdd(v_colors + g * 3 + 2, a[2]);
+                atomicAdd(v_conics + g * 3 + 0, a[3]);
+                atomicAdd(v_conics + g * 3 + 1, a[4] + a[4]);
+                atomicAdd(v_conics + g * 3 + 2, a[5]);
+                atomicAdd(v_means2d + g * 2 + 0, __fmaf_rn(conic.x + conic.x, a[6], conic.y * a[7]));
+                atomicAdd(v_means2d + g * 2 + 1, __fmaf_rn(conic.y, a[6], (conic.z + conic.z) * a[7]));
+                atomicAdd(v_opacities + g, a[8]);
+                atomicAdd(v_betas + g, a[9] * 0.693147180559945f);  // lg2 -> ln
+                acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+}
+
+// 0 = lane-per-pixel kernel with the transposing butterfly, 1 = lane-per-pair kernel (default); UBS_BWD3_VARIANT
+// overrides it for A/B measurements (read once).
+static int bwd3_variant() {
+    static const int v = [] {
+        const char *e = getenv("UBS_BWD3_VARIANT");
+        return e != nullptr ? atoi(e) : 1;
+    }();
+    return v;
+}
+
 template <int CH>
 int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const float *means2d, const float *conics,
                const float *colors, const float *opacities, const float *betas, const float *backgrounds,
@@ -530,6 +937,17 @@ int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
     const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
     dim3 grid(tw, th, (unsigned)C), block(kTilePixels, 1, 1);
     if constexpr (CH == 3) {
+        const int variant = bwd3_variant();
+        if (variant != 0) {
+            auto *k1 = variant == 2 ? rasterize_bwd3_pairlane_kernel<2, 4, false> : rasterize_bwd3_pairlane_kernel<4, 3, false>;
+            k1<<<grid, block, 0, s>>>(
+                C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities, betas, backgrounds, masks,
+                (uint32_t)width, (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids,
+                v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas,
+                (const float4 *)splats, splat_colors != 0, nullptr);
+            UBS_LAUNCH_CHECK("rasterize_bwd_kernel");
+            return UBS_OK;
+        }
         rasterize_bwd3_kernel<<<grid, block, 0, s>>>(
             C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities, betas, backgrounds, masks,
             (uint32_t)width, (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids,
@@ -543,6 +961,22 @@ int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
             (const float4 *)splats, splat_colors != 0, v_depths);
     }
     UBS_LAUNCH_CHECK("rasterize_bwd_kernel");
+    return UBS_OK;
+}
+
+// RGB from the 48-byte splat rows, gradients into 48-byte rows (ubs_rasterize_bwd_rows)
+int launch_bwd_rows(int C, int64_t N, const int64_t *n_isects, int64_t cap, const float *splats,
+                    const float *backgrounds, const uint8_t *masks, int width, int height, const int32_t *offsets,
+                    const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
+                    const float *v_render_colors, const float *v_render_alphas, float *v_rows, cudaStream_t s) {
+    const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
+    dim3 grid(tw, th, (unsigned)C), block(kTilePixels, 1, 1);
+    // four pixels in flight per lane at 3 CTAs / SM measured faster than two at 4 CTAs / SM (1.124 against 1.156 ms, cfg3)
+    rasterize_bwd3_pairlane_kernel<4, 3, true><<<grid, block, 0, s>>>(
+        C, N, n_isects, cap, nullptr, nullptr, nullptr, nullptr, nullptr, backgrounds, masks, (uint32_t)width,
+        (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas,
+        nullptr, nullptr, nullptr, nullptr, nullptr, (const float4 *)splats, true, v_rows);
+    UBS_LAUNCH_CHECK("rasterize_bwd_rows_kernel");
     return UBS_OK;
 }
 
@@ -620,4 +1054,23 @@ extern "C" int ubs_rasterize_bwd_splats(int C, int64_t N, const int64_t *n_isect
                               channels, width, height, tile_size, offsets, flatten_ids, render_alphas, last_ids,
                               v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas,
                               splats, colors == nullptr ? 1 : 0, colors == nullptr ? v_depths : nullptr, stream);
+}
+
+extern "C" int ubs_rasterize_bwd_rows(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity,
+                                      const float *splats, const float *backgrounds, const uint8_t *masks, int width,
+                                      int height, int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
+                                      const float *render_alphas, const int32_t *last_ids,
+                                      const float *v_render_colors, const float *v_render_alphas, float *v_rows,
+                                      void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "rasterize_bwd_rows: bad sizes");
+    UBS_CHECK_ARG(tile_size == kTile, "rasterize_bwd_rows: tile_size must be %d (got %d)", kTile, tile_size);
+    if (C == 0 || N == 0 || isect_capacity == 0) return UBS_OK;  // no pairs: every gradient stays zero
+    UBS_CHECK_ARG(n_isects && offsets && splats && flatten_ids && render_alphas && last_ids && v_render_colors &&
+                      v_render_alphas && v_rows,
+                  "rasterize_bwd_rows: null pointer");
+    UBS_CHECK_ARG((((uintptr_t)splats | (uintptr_t)v_rows) & 15) == 0,
+                  "rasterize_bwd_rows: splats / v_rows must be 16-byte aligned");
+    return launch_bwd_rows(C, N, n_isects, isect_capacity, splats, backgrounds, masks, width, height, offsets, flatten_ids,
+                           render_alphas, last_ids, v_render_colors, v_render_alphas, v_rows, (cudaStream_t)stream);
 }

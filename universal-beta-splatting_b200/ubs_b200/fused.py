@@ -86,8 +86,9 @@ class FusedRasterizer:
 
     def __init__(self, D: int, N: int, width: int, height: int, n_cams: int = 1, capacity: Optional[int] = None,
                  tile_size: int = 16, device="cuda", eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0,
-                 antialiased=False, sort_mode: str = "bin", on_overflow: str = "warn"):
+                 antialiased=False, sort_mode: str = "bin", on_overflow: str = "warn", grad_rows: bool = True):
         self.lib = _lib.load()
+        self.grad_rows = grad_rows  # RGB frames: screen-space gradients as 48-byte rows (False: separate arrays)
         self.D, self.N, self.W, self.H, self.C = D, N, width, height, n_cams
         self.tile_size = tile_size
         self.tw, self.th = math.ceil(width / tile_size), math.ceil(height / tile_size)
@@ -270,8 +271,15 @@ class FusedRasterizer:
         return rc_out, ra_out
 
     def _grad_buffers(self):
+        """Screen-space gradient storage of the frame's mode, to be zeroed before the compositing backward.
+        RGB frames: one 48-byte row per (camera, primitive), v_rows [C, N, 12] (ubs_rasterize_bwd_rows; layout in
+        include/ubs_b200.h).  Depth modes (and grad_rows=False): the separate arrays of ubs_rasterize_bwd_splats."""
+        C, N = self.C, self.N
+        if self.channels == 3 and self.grad_rows:
+            if getattr(self, "v_rows", None) is None:
+                self.v_rows = torch.empty((C, N, 12), dtype=torch.float32, device=self.device)
+            return self.v_rows
         if getattr(self, "_gflat", None) is None:
-            C, N = self.C, self.N
             self._gflat = torch.empty((C * N * 11,), dtype=torch.float32, device=self.device)
             o = 0
             views = []
@@ -281,6 +289,17 @@ class FusedRasterizer:
             self.v_means2d, self.v_conics, self.v_colors, self.v_opacities, self.v_betas, self.v_depths = views
         # the depth gradients (last C N floats) are only produced by the 4- and 1-channel modes
         return self._gflat if self.channels != 3 else self._gflat[:self.C * self.N * 10]
+
+    def grad_args(self, sl: Optional[slice] = None):
+        """The seven gradient-input pointers of ubs_fused_project_bwd* (v_means2d, v_depths, v_conics, v_opacities,
+        v_betas, v_colors, v_rows) for the frame composite_backward() last differentiated; sl = a row range.  The
+        pointers address buffers owned by self (row slices are views at an offset, no temporaries)."""
+        sl = slice(None) if sl is None else sl
+        if self.channels == 3 and self.grad_rows:
+            return (None, None, None, None, None, None, ptr(self.v_rows[:, sl]))
+        return (ptr(self.v_means2d[:, sl]), ptr(self.v_depths[:, sl]) if self.channels != 3 else None,
+                ptr(self.v_conics[:, sl]), ptr(self.v_opacities[:, sl]), ptr(self.v_betas[:, sl]),
+                ptr(self.v_colors[:, sl]), None)
 
     @torch.no_grad()
     def backward(self, records: Tensor, viewmats: Tensor, Ks: Tensor, cam_pos: Tensor, timestamps: Optional[Tensor],
@@ -305,10 +324,8 @@ class FusedRasterizer:
             with self._stage("fused_project_bwd_adam"):
               check(lib.ubs_fused_project_bwd_adam(
                 C, N, D, ptr(records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), self.W, self.H,
-                self.eps2d, 1 if self.aa else 0, ptr(self.radii), ptr(self.conics), ptr(self.v_means2d),
-                ptr(self.v_depths) if self.channels != 3 else None,
-                ptr(self.v_conics), ptr(self.v_opacities), ptr(self.v_betas), ptr(self.v_colors), ptr(adam.exp_avg),
-                ptr(adam.exp_avg_sq), ctypes.cast(cols, ctypes.c_void_p), adam.betas[0], adam.betas[1], adam.eps,
+                self.eps2d, 1 if self.aa else 0, ptr(self.radii), ptr(self.conics), *self.grad_args(),
+                ptr(adam.exp_avg), ptr(adam.exp_avg_sq), ctypes.cast(cols, ctypes.c_void_p), adam.betas[0], adam.betas[1], adam.eps,
                 adam.step_count, float(opacity_reg), float(scale_reg), ptr(self.status), s),
                 "ubs_fused_project_bwd_adam")
             return None
@@ -333,11 +350,18 @@ class FusedRasterizer:
         v_rc, v_ra = v_render_colors.contiguous(), v_render_alphas.contiguous()  # locals: alive until after the launch
         assert v_rc.shape == (C, self.H, self.W, ch) and v_ra.shape == (C, self.H, self.W, 1)
         with self._stage("rasterize_bwd"):
-          check(lib.ubs_rasterize_bwd_splats(
-            C, N, ptr(self.n_isects), self.capacity, ptr(self.splats), None, ptr(backgrounds), None, ch, self.W, self.H,
-            self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(alphas), ptr(self.last_ids),
-            ptr(v_rc), ptr(v_ra), ptr(self.v_means2d), ptr(self.v_conics), ptr(self.v_colors), ptr(self.v_opacities),
-            ptr(self.v_betas), ptr(self.v_depths) if ch != 3 else None, s), "ubs_rasterize_bwd_splats")
+          if ch == 3 and self.grad_rows:
+            check(lib.ubs_rasterize_bwd_rows(
+              C, N, ptr(self.n_isects), self.capacity, ptr(self.splats), ptr(backgrounds), None, self.W, self.H,
+              self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(alphas), ptr(self.last_ids), ptr(v_rc),
+              ptr(v_ra), ptr(self.v_rows), s), "ubs_rasterize_bwd_rows")
+          else:
+            check(lib.ubs_rasterize_bwd_splats(
+              C, N, ptr(self.n_isects), self.capacity, ptr(self.splats), None, ptr(backgrounds), None, ch, self.W,
+              self.H, self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(alphas), ptr(self.last_ids),
+              ptr(v_rc), ptr(v_ra), ptr(self.v_means2d), ptr(self.v_conics), ptr(self.v_colors),
+              ptr(self.v_opacities), ptr(self.v_betas), ptr(self.v_depths) if ch != 3 else None, s),
+              "ubs_rasterize_bwd_splats")
 
     @torch.no_grad()
     def project_backward_rows(self, records, viewmats, Ks, cam_pos, timestamps, v_records, begin: int, count: int,
@@ -352,9 +376,7 @@ class FusedRasterizer:
         check(self.lib.ubs_fused_project_bwd(
             self.C, count, self.D, ptr(records[sl]), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), self.W,
             self.H, self.eps2d, 1 if self.aa else 0, ptr(self.radii[:, sl]), ptr(self.conics[:, sl]),
-            ptr(self.v_means2d[:, sl]), ptr(self.v_depths[:, sl]) if self.channels != 3 else None,
-            ptr(self.v_conics[:, sl]), ptr(self.v_opacities[:, sl]),
-            ptr(self.v_betas[:, sl]), ptr(self.v_colors[:, sl]), ptr(v_records[sl]), 1 if activated else 0,
+            *self.grad_args(sl), ptr(v_records[sl]), 1 if activated else 0,
             ptr(None if query is None else query[sl]), ptr(self.status),
             torch.cuda.current_stream().cuda_stream), "ubs_fused_project_bwd")
 

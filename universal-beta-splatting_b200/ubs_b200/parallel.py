@@ -164,8 +164,7 @@ def sharded_backward_scatter(rz, st: ShardedState, viewmats, Ks, cam_pos, timest
     arr = (ctypes.c_void_p * st.world)(*st.peer_staging)
     check(rz.lib.ubs_fused_project_bwd_scatter(
         st.N, st.D, ptr(st.records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), rz.W, rz.H, rz.eps2d,
-        1 if rz.aa else 0, ptr(rz.radii), ptr(rz.conics), ptr(rz.v_means2d), None, ptr(rz.v_conics),
-        ptr(rz.v_opacities), ptr(rz.v_betas), ptr(rz.v_colors), st.world, st.rank, st.shard_rows,
+        1 if rz.aa else 0, ptr(rz.radii), ptr(rz.conics), *rz.grad_args(), st.world, st.rank, st.shard_rows,
         ctypes.cast(arr, ctypes.c_void_p), ptr(rz.status), torch.cuda.current_stream().cuda_stream),
         "ubs_fused_project_bwd_scatter")
 
