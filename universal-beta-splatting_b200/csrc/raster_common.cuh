@@ -117,4 +117,38 @@ __device__ __forceinline__ uint32_t refine_sub_tile_mask(uint32_t mask, float mx
     }
     return mask;
 }
+// Which (16 / COLS) x 4 pixel blocks of the tile can {sigma < 1} of a conic (a, b, c) centred at (mx, my) touch: bit
+// COLS r + cx = block column cx of block row r (COLS = 2: the eight 8x4 sub-tiles in sub_tile_of's numbering, COLS = 4:
+// sixteen 4x4 blocks).  Exact up to the stated margins: for each of the four block rows, the x-extent of the ellipse
+// restricted to the rows' y-slab (the right edge x = (-b v + sqrt(a - det v^2)) / a is concave in v = y - my with its
+// maximum at v* = -b / sqrt(det c); the left edge mirrors it), compared with the block columns.  (tx0, ty0) = centre
+// of the tile's first pixel.  Degenerate conics are never culled.
+template <int COLS>
+__device__ __forceinline__ uint32_t slab_mask(float mx, float my, float a, float b, float c, float tx0, float ty0) {
+    constexpr int CW = kTile / COLS, RH = 4;
+    const float det = a * c - b * b;
+    if (!(det > 0.f && a > 0.f && c > 0.f)) return (1u << (4 * COLS)) - 1u;
+    const float hy = sqrtf(a / det);
+    const float vstar = -b * rsqrtf(det * c);
+    const float ra = 1.f / a;
+    const float u0 = tx0 - mx;  // first pixel column relative to the centre
+    uint32_t mask = 0;
+#pragma unroll
+    for (int r = 0; r < kTile / RH; ++r) {
+        const float d0 = ty0 + (float)(RH * r) - my;
+        const float lo = fmaxf(d0 - 0.01f, -hy), hi = fminf(d0 + (float)(RH - 1) + 0.01f, hy);
+        if (lo > hi) continue;
+        const float vr = fminf(fmaxf(vstar, lo), hi), vl = fminf(fmaxf(-vstar, lo), hi);
+        float xr = (sqrtf(fmaxf(0.f, a - det * vr * vr)) - b * vr) * ra;
+        float xl = (-sqrtf(fmaxf(0.f, a - det * vl * vl)) - b * vl) * ra;
+        xr += 0.01f + 0.001f * fabsf(xr);
+        xl -= 0.01f + 0.001f * fabsf(xl);
+        uint32_t cols = 0;
+#pragma unroll
+        for (int cx = 0; cx < COLS; ++cx)
+            if (xl <= u0 + (float)(CW * cx + CW - 1) && xr >= u0 + (float)(CW * cx)) cols |= 1u << cx;
+        mask |= cols << (COLS * r);
+    }
+    return mask;
+}
 }  // namespace ubs

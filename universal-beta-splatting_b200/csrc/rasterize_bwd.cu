@@ -540,37 +540,6 @@ rasterize_bwd3_kernel(int C, int64_t N, const int64_t *__restrict__ n_isects_dev
 constexpr int kBlk = 4;                     // block edge in pixels
 constexpr int kBlkPix = kBlk * kBlk;        // 16 pixels per block, 16 blocks per tile: bit (by * 4 + bx) of a pair's mask
 
-// Which 4x4 blocks of the tile can {sigma < 1} of a conic (a, b, c) centred at (mx, my) touch.  Exact up to the stated
-// margins: for each of the four block rows, the x-extent of the ellipse restricted to the rows' y-slab (the right edge
-// x = (-b v + sqrt(a - det v^2)) / a is concave in v = y - my with its maximum at v* = -b / sqrt(det c); the left edge
-// mirrors it), compared with the four block columns.  (tx0, ty0) = centre of the tile's first pixel.
-__device__ __forceinline__ uint32_t block_mask16(float mx, float my, float a, float b, float c, float tx0, float ty0) {
-    const float det = a * c - b * b;
-    if (!(det > 0.f && a > 0.f && c > 0.f)) return 0xFFFFu;  // degenerate conic: never culled
-    const float hy = sqrtf(a / det);
-    const float vstar = -b * rsqrtf(det * c);
-    const float ra = 1.f / a;
-    const float u0 = tx0 - mx;  // first pixel column relative to the centre
-    uint32_t mask = 0;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const float d0 = ty0 + (float)(kBlk * r) - my;
-        const float lo = fmaxf(d0 - 0.01f, -hy), hi = fminf(d0 + (float)(kBlk - 1) + 0.01f, hy);
-        if (lo > hi) continue;
-        const float vr = fminf(fmaxf(vstar, lo), hi), vl = fminf(fmaxf(-vstar, lo), hi);
-        float xr = (sqrtf(fmaxf(0.f, a - det * vr * vr)) - b * vr) * ra;
-        float xl = (-sqrtf(fmaxf(0.f, a - det * vl * vl)) - b * vl) * ra;
-        xr += 0.01f + 0.001f * fabsf(xr);
-        xl -= 0.01f + 0.001f * fabsf(xl);
-        uint32_t cols = 0;
-#pragma unroll
-        for (int cx = 0; cx < 4; ++cx)
-            if (xl <= u0 + (float)(kBlk * cx + kBlk - 1) && xr >= u0 + (float)(kBlk * cx)) cols |= 1u << cx;
-        mask |= cols << (4 * r);
-    }
-    return mask;
-}
-
 // shfl.sync.up inside W-lane segments as a volatile asm statement: the compiler keeps volatile statements in source order,
 // which is what interleaves the scans of independent pixels (left alone it finishes one scan before starting the next)
 template <int W>
@@ -591,7 +560,11 @@ __device__ __forceinline__ void red_add_v2(float *p, float a, float b) {
 // One bucket: lanes j = lane % W hold the pairs list[0 .. n), n <= W; 32 / W pixels of the block are processed per step and
 // NCH steps (independent pixels) are advanced together: the shuffles of their scans are issued stage by stage for all of
 // them, so that one chain's SHFL latency is covered by the others (the compiler keeps shuffles in source order).
-template <int W, int NCH, bool ROWS_OUT>
+// Per (pair, pixel), with R = 1 / (1 - alpha) and T' = T R the transmittance in front of the pair
+// (rasterize_to_pixels_bwd.cu:190-245 in closed form):
+//     v_alpha = T' cv - R (sum_behind - Kc)  =  R (T' cv + Kc - B_after),      B_after = B_before + alpha T' cv,
+// since 1 + alpha R = R; and alpha R = R - 1 gives the scan element K = (R - 1) cv with one FFMA.
+template <int W, int NCH_, bool ROWS_OUT>
 __device__ __forceinline__ void pairlane_bucket(uint32_t lane, const uint8_t *__restrict__ list, int32_t n,
                                                 const Staged3 *__restrict__ s_rec, float *__restrict__ s_acc,
                                                 const int32_t *__restrict__ s_id, float *__restrict__ v_rows,
@@ -600,51 +573,59 @@ __device__ __forceinline__ void pairlane_bucket(uint32_t lane, const uint8_t *__
     constexpr int G = 32 / W;                  // pixels per step
     constexpr int STEPS = kBlkPix / G;         // steps per block (W = 32: 16, 16: 8, 8: 4)
     constexpr int XS = kBlk / G;               // steps per pixel row (W = 32: 4, 16: 2, 8: 1)
-    static_assert(STEPS % NCH == 0, "chains per iteration must divide the steps of a block");
+    constexpr int NCH = NCH_ < STEPS ? NCH_ : STEPS;
+    static_assert(STEPS % NCH == 0 && NCH % XS == 0, "an iteration covers whole pixel rows of the block");
+    constexpr int ROWS = NCH / XS;             // pixel rows per iteration
     const uint32_t j = lane & (W - 1), ph = lane / W;
     const bool has = (int32_t)j < n;
     const uint32_t slot = has ? (uint32_t)list[j] : (uint32_t)kTilePixels;  // [kTilePixels] = the NaN sentinel
     const float4 xyob = s_rec[slot].xyob, conic = s_rec[slot].conic, col = s_rec[slot].col;
     const int32_t pair_idx = batch_end - (int32_t)slot;  // position of the pair in the sorted list
+    const float neg_beta = -xyob.w;
     float acc[kGrad3];
 #pragma unroll
     for (int k = 0; k < kGrad3; ++k) acc[k] = 0.f;
-    const float px0 = pxb + (float)ph;  // G > 1: the lane's pixel column inside a step
+    // the columns of the steps of an iteration are the same in every iteration: their share of sigma is formed once
+    // (sigma = fma(dy, dx (2b), fma(dx, a dx, dy (c dy))): the association of the forward pass, bit for bit)
+    float dxc[XS], adx[XS], bdx[XS];
+#pragma unroll
+    for (int xs = 0; xs < XS; ++xs) {
+        dxc[xs] = xyob.x - (pxb + (float)(ph + xs * G));
+        adx[xs] = conic.x * dxc[xs];
+        bdx[xs] = dxc[xs] * conic.y;
+    }
     const float4 *pc_it = pix_const + ph;
     float4 *ps_it = pix_state + ph;
-    float py0 = pyb, px_it = px0;  // px_it: first column of the iteration when a pixel row takes several iterations
-    constexpr int ROWS = NCH >= XS ? NCH / XS : 1;  // pixel rows per iteration
+    float py0 = pyb;
 #pragma unroll 1
     for (int it = 0; it < STEPS / NCH; ++it) {
         float4 pc[NCH];
-        float T0[NCH], B0[NCH], dx[NCH], dy[NCH], alpha[NCH], ra[NCH], cv[NCH], lg[NCH], vis_g[NCH], w_g[NCH], ov_g[NCH];
+        float T0[NCH], B0[NCH], dyr[ROWS], cdy2[ROWS], ra[NCH], cv[NCH], lg[NCH], vis[NCH], ov[NCH], rom[NCH];
         float R[NCH], K[NCH];
 #pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            dyr[r] = xyob.y - (py0 + (float)r);
+            cdy2[r] = dyr[r] * (conic.z * dyr[r]);
+        }
+#pragma unroll
         for (int t = 0; t < NCH; ++t) {
-            // step s = it * NCH + t covers pixel s * G + ph of the block: column (s % XS) * G + ph, row s / XS
-            const int xs = NCH >= XS ? t % XS : -1, row = NCH >= XS ? t / XS : 0;
-            const int pix = NCH >= XS ? row * kBlk + xs * G : t * G;  // offset from pc_it (NCH < XS: part of one row)
-            pc[t] = pc_it[pix];  // v_r, v_g, v_b, Kc
+            // step it * NCH + t covers pixel column (t % XS) * G + ph of row it * ROWS + t / XS of the block
+            const int xs = t % XS, row = t / XS;
+            const int pix = row * kBlk + xs * G;
+            pc[t] = pc_it[pix];            // v_r, v_g, v_b, Kc
             const float4 ps = ps_it[pix];  // T, B, last_ids
             T0[t] = ps.x, B0[t] = ps.y;
-            const float px = (NCH >= XS ? px0 : px_it) + (float)((NCH >= XS ? xs : t) * G);
-            const float py = py0 + (float)row;
-            dx[t] = xyob.x - px, dy[t] = xyob.y - py;
-            const float sigma = __fmaf_rn(dy[t], dx[t] * conic.y, __fmaf_rn(dx[t], conic.x * dx[t], dy[t] * (conic.z * dy[t])));
+            const float sigma = __fmaf_rn(dyr[row], bdx[xs], __fmaf_rn(dxc[xs], adx[xs], cdy2[row]));
             // sigma in [0, 1) and the pair not behind this pixel's last contributor (rasterize_to_pixels_bwd.cu:166-168)
             const bool valid = (__float_as_uint(sigma) < 0x3f800000u) && (pair_idx <= __float_as_int(ps.z));
             const float om = 1.f - (valid ? sigma : 0.f);
             lg[t] = __log2f(om);
-            const float vis = valid ? exp2f(xyob.w * lg[t]) : 0.f;
-            const float ov = xyob.z * vis;
-            alpha[t] = fminf(0.999f, ov);
-            ra[t] = fast_rcp(1.f - alpha[t]);
+            vis[t] = valid ? exp2f(xyob.w * lg[t]) : 0.f;
+            ov[t] = xyob.z * vis[t];
+            rom[t] = fast_rcp(om);
+            ra[t] = fast_rcp(1.f - fminf(0.999f, ov[t]));
             cv[t] = __fmaf_rn(col.z, pc[t].z, __fmaf_rn(col.y, pc[t].y, col.x * pc[t].x));
-            const bool live = ov <= 0.999f;  // the clamp has zero slope above it (rasterize_to_pixels_bwd.cu:230)
-            ov_g[t] = live ? ov : 0.f;
-            vis_g[t] = live ? vis : 0.f;
-            w_g[t] = ov_g[t] * fast_rcp(om);  // o beta (1-sigma)^(beta-1) = beta ov / (1-sigma)
-            R[t] = ra[t], K[t] = (alpha[t] * ra[t]) * cv[t];
+            R[t] = ra[t], K[t] = __fmaf_rn(ra[t], cv[t], -cv[t]);  // alpha R cv
         }
         // inclusive scans of (R, K) over the pairs of the bucket, furthest back first; all chains stage by stage
 #pragma unroll
@@ -665,35 +646,30 @@ __device__ __forceinline__ void pairlane_bucket(uint32_t lane, const uint8_t *__
         }
 #pragma unroll
         for (int t = 0; t < NCH; ++t) {
-            const int xs = NCH >= XS ? t % XS : -1, row = NCH >= XS ? t / XS : 0;
-            const int pix = NCH >= XS ? row * kBlk + xs * G : t * G;
-            const float Tl = T0[t] * R[t];                      // transmittance in front of this pair
-            const float fac = alpha[t] * Tl;
-            const float B_after = __fmaf_rn(T0[t], K[t], B0[t]);   // sum_k buffer[k] v_rc[k] including this pair
-            const float B_before = __fmaf_rn(-fac, cv[t], B_after);
+            const int xs = t % XS, row = t / XS;
+            const int pix = row * kBlk + xs * G;
+            const float Tl = T0[t] * R[t];                        // transmittance in front of this pair
+            const float B_after = __fmaf_rn(T0[t], K[t], B0[t]);  // sum_k buffer[k] v_rc[k] including this pair
             if (j == W - 1) *reinterpret_cast<float2 *>(ps_it + pix) = make_float2(Tl, B_after);
-            const float v_alpha = __fmaf_rn(Tl, cv[t], ra[t] * (pc[t].w - B_before));
+            const float fac = fminf(0.999f, ov[t]) * Tl;
             acc[0] = __fmaf_rn(fac, pc[t].x, acc[0]);
             acc[1] = __fmaf_rn(fac, pc[t].y, acc[1]);
             acc[2] = __fmaf_rn(fac, pc[t].z, acc[2]);
-            const float v_sigma = -(v_alpha * xyob.w) * w_g[t];
-            const float tx = dx[t] * v_sigma, ty = dy[t] * v_sigma;
-            acc[3] = __fmaf_rn(tx, dx[t], acc[3]);
-            acc[4] = __fmaf_rn(tx, dy[t], acc[4]);
-            acc[5] = __fmaf_rn(ty, dy[t], acc[5]);
+            float v_alpha = ra[t] * __fmaf_rn(Tl, cv[t], pc[t].w - B_after);
+            v_alpha = ov[t] <= 0.999f ? v_alpha : 0.f;  // the clamp has zero slope above it (rasterize_to_pixels_bwd.cu:230)
+            acc[8] = __fmaf_rn(vis[t], v_alpha, acc[8]);
+            const float u = v_alpha * ov[t];
+            acc[9] = __fmaf_rn(u, lg[t], acc[9]);
+            const float v_sigma = (u * rom[t]) * neg_beta;  // d alpha / d sigma = -o beta (1 - sigma)^(beta - 1)
+            const float tx = dxc[xs] * v_sigma, ty = dyr[row] * v_sigma;
+            acc[3] = __fmaf_rn(tx, dxc[xs], acc[3]);
+            acc[4] = __fmaf_rn(tx, dyr[row], acc[4]);
+            acc[5] = __fmaf_rn(ty, dyr[row], acc[5]);
             acc[6] += tx;
             acc[7] += ty;
-            acc[8] = __fmaf_rn(vis_g[t], v_alpha, acc[8]);
-            acc[9] = __fmaf_rn(v_alpha * ov_g[t], lg[t], acc[9]);
         }
-        if constexpr (NCH >= XS) {
-            py0 += (float)ROWS;
-            pc_it += ROWS * kBlk, ps_it += ROWS * kBlk;
-        } else {
-            if ((it + 1) % (XS / NCH) == 0) py0 += 1.f, px_it = px0;
-            else px_it += (float)(NCH * G);
-            pc_it += NCH * G, ps_it += NCH * G;
-        }
+        py0 += (float)ROWS;
+        pc_it += ROWS * kBlk, ps_it += ROWS * kBlk;
     }
     if constexpr (G > 1) {  // the segments hold the same pairs: add their sums
 #pragma unroll
@@ -830,7 +806,7 @@ rasterize_bwd3_pairlane_kernel(int C, int64_t N, const int64_t *__restrict__ n_i
             s_rec[tr].xyob = xyob;
             s_rec[tr].conic = make_float4(ca, cb + cb, cc, 0.f);
             s_rec[tr].col = col;
-            s_mask[tr] = (uint16_t)block_mask16(xyob.x, xyob.y, ca, cb, cc, tx0, ty0);
+            s_mask[tr] = (uint16_t)slab_mask<4>(xyob.x, xyob.y, ca, cb, cc, tx0, ty0);
         } else {
             s_mask[tr] = 0;
         }
@@ -939,7 +915,7 @@ int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
     if constexpr (CH == 3) {
         const int variant = bwd3_variant();
         if (variant != 0) {
-            auto *k1 = variant == 2 ? rasterize_bwd3_pairlane_kernel<2, 4, false> : rasterize_bwd3_pairlane_kernel<4, 3, false>;
+            auto *k1 = rasterize_bwd3_pairlane_kernel<4, 3, false>;
             k1<<<grid, block, 0, s>>>(
                 C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities, betas, backgrounds, masks,
                 (uint32_t)width, (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids,
@@ -972,7 +948,8 @@ int launch_bwd_rows(int C, int64_t N, const int64_t *n_isects, int64_t cap, cons
     const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
     dim3 grid(tw, th, (unsigned)C), block(kTilePixels, 1, 1);
     // four pixels in flight per lane at 3 CTAs / SM measured faster than two at 4 CTAs / SM (1.124 against 1.156 ms, cfg3)
-    rasterize_bwd3_pairlane_kernel<4, 3, true><<<grid, block, 0, s>>>(
+    auto *kern = bwd3_variant() == 8 ? rasterize_bwd3_pairlane_kernel<8, 2, true> : rasterize_bwd3_pairlane_kernel<4, 3, true>;
+    kern<<<grid, block, 0, s>>>(
         C, N, n_isects, cap, nullptr, nullptr, nullptr, nullptr, nullptr, backgrounds, masks, (uint32_t)width,
         (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas,
         nullptr, nullptr, nullptr, nullptr, nullptr, (const float4 *)splats, true, v_rows);
