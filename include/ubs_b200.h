@@ -224,7 +224,8 @@ int ubs_rasterize_bwd_splats(int C, int64_t N, const int64_t *n_isects, int64_t 
  *   0..2  v_colors            3, 4, 5  v_conics = (r3, 2 r4, r5)
  *   6, 7  moment form of v_means2d = (2a r6 + 2b r7, 2b r6 + 2c r7) with the primitive's conic (a, b, c)
  *   8     v_opacities         9  v_betas / ln 2        10  v_depths (not written here)        11  unused
- * ubs_fused_project_bwd* take these rows as `v_rows` (two sectors per visible primitive instead of eight).
+ * ubs_fused_project_bwd* take these rows as `v_rows` with rows_form = 1 (two sectors per visible primitive instead
+ * of the eight of separate arrays).
  * Same results as ubs_rasterize_bwd_splats(channels = 3) up to the order of the float additions
  * (replaces rasterize_to_pixels_bwd.cu:106-274 for the (16-tile, 3-channel) instantiation).                     */
 int ubs_rasterize_bwd_rows(int C, int64_t N, const int64_t *n_isects, int64_t isect_capacity, const float *splats,
@@ -232,6 +233,12 @@ int ubs_rasterize_bwd_rows(int C, int64_t N, const int64_t *n_isects, int64_t is
                            const int32_t *offsets, const int32_t *flatten_ids, const float *render_alphas,
                            const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
                            float *v_rows, void *stream);
+/* Rows for ubs_fused_project_bwd* (rows_form = 0) from the separate gradient arrays of ubs_rasterize_bwd[_splats]:
+ * 0..2 v_colors | 3..5 v_conics | 6, 7 v_means2d | 8 v_opacities | 9 v_betas | 10 v_depths | 11 zero.
+ * v_colors / v_depths may be NULL (zeros).  CN = C * N.                                                          */
+int ubs_pack_gradient_rows(int64_t CN, const float *v_means2d, const float *v_depths, const float *v_conics,
+                           const float *v_opacities, const float *v_betas, const float *v_colors, float *v_rows,
+                           void *stream);
 int ubs_rasterize_count(int C, const int64_t *n_isects, int64_t isect_capacity, const float *means2d,
                         const float *conics, const float *opacities, const float *betas, int width, int height,
                         int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
@@ -292,10 +299,9 @@ int ubs_fused_project_fwd(int C, int64_t N, int D, const float *records, /* [N, 
 int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const float *viewmats, const float *Ks,
                           const float *cam_pos, const float *timestamps, int width, int height, float eps2d,
                           int calc_compensations, const int32_t *radii, const float *conics,
-                          const float *v_means2d, const float *v_depths, const float *v_conics,
-                          const float *v_opacities, const float *v_betas, const float *v_colors, /* [C,N,3] or NULL */
-                          const float *v_rows, /* NULL, or [C,N,12] rows of ubs_rasterize_bwd_rows: then read INSTEAD
-                                                  of the six v_* arrays (which may be NULL) */
+                          const float *v_rows, /* [C,N,12] screen-space gradient rows */
+                          int rows_form,       /* 1: as ubs_rasterize_bwd_rows writes them (moment form),
+                                                  0: as ubs_pack_gradient_rows builds them from separate arrays */
                           float *v_records,    /* [N, stride] */
                           int activated, const float *query, /* as in ubs_fused_project_fwd */
                           const int32_t *skip_flag, /* NULL, or the `status` of the frame's tile-list build: when
@@ -342,9 +348,7 @@ int ubs_adam_step(int64_t N, int D, int64_t row_begin, int64_t row_count, /* upd
 int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *records, const float *viewmats, const float *Ks,
                                const float *cam_pos, const float *timestamps, int width, int height, float eps2d,
                                int calc_compensations, const int32_t *radii, const float *conics,
-                               const float *v_means2d, const float *v_depths, const float *v_conics,
-                               const float *v_opacities, const float *v_betas, const float *v_colors,
-                               const float *v_rows, /* as in ubs_fused_project_bwd */
+                               const float *v_rows, int rows_form, /* as in ubs_fused_project_bwd */
                                float *exp_avg, float *exp_avg_sq, const double *h_lr, double beta1, double beta2, double eps,
                                int64_t step, double opacity_reg, double scale_reg,
                                const int32_t *skip_flag, /* as above; a truncated frame leaves records and moments
@@ -364,9 +368,7 @@ int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *records, const fl
 int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *records, const float *viewmats, const float *Ks,
                                   const float *cam_pos, const float *timestamps, int width, int height, float eps2d,
                                   int calc_compensations, const int32_t *radii, const float *conics,
-                                  const float *v_means2d, const float *v_depths, const float *v_conics,
-                                  const float *v_opacities, const float *v_betas, const float *v_colors,
-                                  const float *v_rows, /* as in ubs_fused_project_bwd */
+                                  const float *v_rows, int rows_form, /* as in ubs_fused_project_bwd */
                                   int world, int rank, int64_t shard_rows, float *const *h_staging,
                                   const int32_t *skip_flag, /* as in ubs_fused_project_bwd: zero tiles are sent */
                                   void *stream);

@@ -265,7 +265,8 @@ struct BwdOpts {
     int activated;             // records hold activated values (see decode_record): no activation derivative
     const float *query;        // NULL, or [N, D-3] queries given by the caller instead of the view direction
     const int32_t *skip_flag;  // NULL, or the `status` word of the frame's tile-list build
-    const float *v_rows;       // NULL, or the 48-byte gradient rows of ubs_rasterize_bwd_rows (then instead of v_*)
+    const float *v_rows;       // [C, N, 12] screen-space gradient rows (layout: include/ubs_b200.h)
+    int moment_form;           // rows of ubs_rasterize_bwd_rows (1) or of ubs_pack_gradient_rows (0)
 };
 
 // Backward of fused_project_fwd_kernel: one thread per primitive, looping over cameras, so the per-primitive sums
@@ -282,9 +283,6 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
                          const float *__restrict__ Ks, const float *__restrict__ cam_pos,
                          const float *__restrict__ timestamps, uint32_t width, uint32_t height, float eps2d,
                          int calc_comp, const int32_t *__restrict__ radii, const float *__restrict__ conics,
-                         const float *__restrict__ v_means2d, const float *__restrict__ v_depths,
-                         const float *__restrict__ v_conics, const float *__restrict__ v_opacities,
-                         const float *__restrict__ v_betas, const float *__restrict__ v_colors,
                          float *__restrict__ v_records, float *__restrict__ exp_avg,
                          float *__restrict__ exp_avg_sq, const AdamParams adam, const ScatterDst scatter,
                          const BwdOpts opts) {
@@ -338,21 +336,8 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
                 const int64_t idx = (int64_t)(cid - 1) * N + base + threadIdx.x;
                 prefetch_l1(conics + idx * 3);
                 prefetch_l1(conics + idx * 3 + 2);
-                if (opts.v_rows != nullptr) {  // one 48-byte row: two sectors
-                    prefetch_l1(opts.v_rows + idx * 12);
-                    prefetch_l1(opts.v_rows + idx * 12 + 8);
-                } else {
-                    prefetch_l1(v_means2d + idx * 2);
-                    prefetch_l1(v_conics + idx * 3);
-                    prefetch_l1(v_conics + idx * 3 + 2);
-                    prefetch_l1(v_opacities + idx);
-                    prefetch_l1(v_betas + idx);
-                    if (v_colors != nullptr) {
-                        prefetch_l1(v_colors + idx * 3);
-                        prefetch_l1(v_colors + idx * 3 + 2);
-                    }
-                    if (v_depths != nullptr) prefetch_l1(v_depths + idx);
-                }
+                prefetch_l1(opts.v_rows + idx * 12);  // one 48-byte row: two sectors
+                prefetch_l1(opts.v_rows + idx * 12 + 8);
             }
         }
         const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -461,28 +446,18 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
             cond_apply<Cd>(prep, xyz, x, o_in, beta_c, mean, o_cond);
 
             const float conic[3] = {conics[idx * 3], conics[idx * 3 + 1], conics[idx * 3 + 2]};
-            float vm[2], vc[3], v_o, v_b, v_d, v_col[3];
-            if (opts.v_rows != nullptr) {  // layout: include/ubs_b200.h, ubs_rasterize_bwd_rows
-                const float4 *row = reinterpret_cast<const float4 *>(opts.v_rows + idx * 12);
-                const float4 q0 = row[0], q1 = row[1], q2 = row[2];
-                v_col[0] = q0.x, v_col[1] = q0.y, v_col[2] = q0.z;
-                vc[0] = q0.w, vc[1] = q1.x + q1.x, vc[2] = q1.y;
-                const float a2 = conic[0] + conic[0], b2 = conic[1] + conic[1], c2 = conic[2] + conic[2];
-                vm[0] = __fmaf_rn(a2, q1.z, b2 * q1.w);
-                vm[1] = __fmaf_rn(b2, q1.z, c2 * q1.w);
-                v_o = q2.x, v_b = q2.y * 0.693147180559945f, v_d = q2.z;
-            } else {
-                vm[0] = v_means2d[idx * 2], vm[1] = v_means2d[idx * 2 + 1];
-                vc[0] = v_conics[idx * 3], vc[1] = v_conics[idx * 3 + 1], vc[2] = v_conics[idx * 3 + 2];
-                v_o = v_opacities[idx], v_b = v_betas[idx];
-                v_d = v_depths != nullptr ? v_depths[idx] : 0.f;
-                if (v_colors != nullptr) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) v_col[k] = v_colors[idx * 3 + k];
-                } else {
-                    v_col[0] = v_col[1] = v_col[2] = 0.f;
-                }
-            }
+            // one 48-byte gradient row; the two forms differ in three slots (selects, no branch: the code below is the
+            // same in every instantiation, which keeps the ADAM and plain kernels bit-identical)
+            const float4 *row = reinterpret_cast<const float4 *>(opts.v_rows + idx * 12);
+            const float4 q0 = row[0], q1 = row[1], q2 = row[2];
+            const bool moment = opts.moment_form != 0;
+            const float v_col[3] = {q0.x, q0.y, q0.z};
+            const float vc[3] = {q0.w, moment ? q1.x + q1.x : q1.x, q1.y};
+            const float a2 = conic[0] + conic[0], b2 = conic[1] + conic[1], c2 = conic[2] + conic[2];
+            const float vm[2] = {moment ? __fmaf_rn(a2, q1.z, __fmul_rn(b2, q1.w)) : q1.z,
+                                 moment ? __fmaf_rn(b2, q1.z, __fmul_rn(c2, q1.w)) : q1.w};
+            float v_o = q2.x;
+            const float v_b = moment ? __fmul_rn(q2.y, 0.693147180559945f) : q2.y, v_d = q2.z;
             float comp = 0.f, v_comp = 0.f;
             if (calc_comp) {
                 const Splat2D f = project_splat(cam, mean, s6, width, height, eps2d, -3.0e38f, 3.0e38f, -1.f);
@@ -686,16 +661,14 @@ extern "C" int ubs_fused_project_fwd(int C, int64_t N, int D, const float *recor
 extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const float *viewmats,
                                      const float *Ks, const float *cam_pos, const float *timestamps, int width,
                                      int height, float eps2d, int calc_compensations, const int32_t *radii,
-                                     const float *conics, const float *v_means2d, const float *v_depths,
-                                     const float *v_conics, const float *v_opacities, const float *v_betas,
-                                     const float *v_colors, const float *v_rows, float *v_records, int activated, const float *query,
+                                     const float *conics, const float *v_rows, int rows_form, float *v_records, int activated, const float *query,
                                      const int32_t *skip_flag, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "fused_project_bwd: bad sizes");
     UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd: D must be 6 or 7 (got %d)", D);
     if (N == 0) return UBS_OK;
     UBS_CHECK_ARG(records && viewmats && Ks && (cam_pos || query) && radii && conics &&
-                      (v_rows || (v_means2d && v_conics && v_opacities && v_betas)) && v_records,
+                      v_rows && v_records,
                   "fused_project_bwd: null pointer");
     UBS_CHECK_ARG(D != 7 || timestamps != nullptr || query != nullptr, "fused_project_bwd: D=7 needs timestamps");
     UBS_CHECK_ARG((((uintptr_t)records | (uintptr_t)v_records) & 15) == 0,
@@ -707,16 +680,16 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
     const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams unused{};
     const ScatterDst no_scatter{};
-    const BwdOpts opts{activated, query, skip_flag, v_rows};
+    const BwdOpts opts{activated, query, skip_flag, v_rows, rows_form};
     if (D == 6)
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
-            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records,
+            calc_compensations, radii, conics, v_records,
             nullptr, nullptr, unused, no_scatter, opts);
     else
         fused_project_bwd_kernel<7, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
-            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, v_records,
+            calc_compensations, radii, conics, v_records,
             nullptr, nullptr, unused, no_scatter, opts);
     UBS_LAUNCH_CHECK("fused_project_bwd_kernel");
     return UBS_OK;
@@ -725,9 +698,7 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
 extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *records, const float *viewmats,
                                           const float *Ks, const float *cam_pos, const float *timestamps, int width,
                                           int height, float eps2d, int calc_compensations, const int32_t *radii,
-                                          const float *conics, const float *v_means2d, const float *v_depths,
-                                          const float *v_conics, const float *v_opacities, const float *v_betas,
-                                          const float *v_colors, const float *v_rows, float *exp_avg, float *exp_avg_sq, const double *h_lr,
+                                          const float *conics, const float *v_rows, int rows_form, float *exp_avg, float *exp_avg_sq, const double *h_lr,
                                           double beta1, double beta2, double eps, int64_t step, double opacity_reg,
                                           double scale_reg, const int32_t *skip_flag, void *stream) {
     using namespace ubs;
@@ -735,7 +706,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
     UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd_adam: D must be 6 or 7 (got %d)", D);
     if (N == 0) return UBS_OK;
     UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && conics &&
-                      (v_rows || (v_means2d && v_conics && v_opacities && v_betas)) && exp_avg && exp_avg_sq && h_lr,
+                      v_rows && exp_avg && exp_avg_sq && h_lr,
                   "fused_project_bwd_adam: null pointer");
     UBS_CHECK_ARG(D != 7 || timestamps != nullptr, "fused_project_bwd_adam: D=7 needs timestamps");
     UBS_CHECK_ARG(step >= 1, "fused_project_bwd_adam: step counts from 1 (got %lld)", (long long)step);
@@ -745,7 +716,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
     const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
     const size_t smem = (size_t)3 * kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
-    const BwdOpts opts{0, nullptr, skip_flag, v_rows};
+    const BwdOpts opts{0, nullptr, skip_flag, v_rows, rows_form};
     if (D == 6) {
         UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<6, 3, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -753,7 +724,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
                                           cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         fused_project_bwd_kernel<6, 3, true><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
-            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
+            calc_compensations, radii, conics, nullptr,
             exp_avg, exp_avg_sq, a, ScatterDst{}, opts);
     } else {
         UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<7, 3, true>,
@@ -762,7 +733,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
                                           cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         fused_project_bwd_kernel<7, 3, true><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
-            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
+            calc_compensations, radii, conics, nullptr,
             exp_avg, exp_avg_sq, a, ScatterDst{}, opts);
     }
     UBS_LAUNCH_CHECK("fused_project_bwd_adam_kernel");
@@ -772,9 +743,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
 extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *records, const float *viewmats,
                                              const float *Ks, const float *cam_pos, const float *timestamps,
                                              int width, int height, float eps2d, int calc_compensations,
-                                             const int32_t *radii, const float *conics, const float *v_means2d,
-                                             const float *v_depths, const float *v_conics, const float *v_opacities,
-                                             const float *v_betas, const float *v_colors, const float *v_rows, int world, int rank,
+                                             const int32_t *radii, const float *conics, const float *v_rows, int rows_form, int world, int rank,
                                              int64_t shard_rows, float *const *h_staging, const int32_t *skip_flag,
                                              void *stream) {
     using namespace ubs;
@@ -786,7 +755,7 @@ extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *reco
                   "fused_project_bwd_scatter: shard_rows must be a positive multiple of %d covering N", kFusedThreads);
     if (N == 0) return UBS_OK;
     UBS_CHECK_ARG(records && viewmats && Ks && cam_pos && radii && conics &&
-                      (v_rows || (v_means2d && v_conics && v_opacities && v_betas)) && h_staging,
+                      v_rows && h_staging,
                   "fused_project_bwd_scatter: null pointer");
     UBS_CHECK_ARG(D != 7 || timestamps != nullptr, "fused_project_bwd_scatter: D=7 needs timestamps");
     ScatterDst sc{};
@@ -801,16 +770,16 @@ extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *reco
     const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
     const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams unused{};
-    const BwdOpts opts{0, nullptr, skip_flag, v_rows};
+    const BwdOpts opts{0, nullptr, skip_flag, v_rows, rows_form};
     if (D == 6)
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             1, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
-            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
+            calc_compensations, radii, conics, nullptr,
             nullptr, nullptr, unused, sc, opts);
     else
         fused_project_bwd_kernel<7, 3, false><<<gx, kFusedThreads, smem, s>>>(
             1, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
-            calc_compensations, radii, conics, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, nullptr,
+            calc_compensations, radii, conics, nullptr,
             nullptr, nullptr, unused, sc, opts);
     UBS_LAUNCH_CHECK("fused_project_bwd_scatter_kernel");
     return UBS_OK;

@@ -73,6 +73,33 @@ int launch_pack(int64_t N, int D, const PackSegs &segs, float *records, cudaStre
     return UBS_OK;
 }
 
+// Separate screen-space gradient arrays -> 48-byte gradient rows in the "direct" form (rows_form = 0 of
+// ubs_fused_project_bwd*): one thread per (camera, primitive); a plain streaming pass (40-44 B read, 48 B written).
+__global__ void __launch_bounds__(256)
+pack_gradient_rows_kernel(int64_t CN, const float *__restrict__ v_means2d, const float *__restrict__ v_depths,
+                          const float *__restrict__ v_conics, const float *__restrict__ v_opacities,
+                          const float *__restrict__ v_betas, const float *__restrict__ v_colors,
+                          float4 *__restrict__ v_rows) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CN) return;
+    float4 q0, q1, q2;
+    q0.x = v_colors != nullptr ? v_colors[i * 3 + 0] : 0.f;
+    q0.y = v_colors != nullptr ? v_colors[i * 3 + 1] : 0.f;
+    q0.z = v_colors != nullptr ? v_colors[i * 3 + 2] : 0.f;
+    q0.w = v_conics[i * 3 + 0];
+    q1.x = v_conics[i * 3 + 1];
+    q1.y = v_conics[i * 3 + 2];
+    q1.z = v_means2d[i * 2 + 0];
+    q1.w = v_means2d[i * 2 + 1];
+    q2.x = v_opacities[i];
+    q2.y = v_betas[i];
+    q2.z = v_depths != nullptr ? v_depths[i] : 0.f;
+    q2.w = 0.f;
+    v_rows[i * 3 + 0] = q0;
+    v_rows[i * 3 + 1] = q1;
+    v_rows[i * 3 + 2] = q2;
+}
+
 }  // namespace
 }  // namespace ubs
 
@@ -100,4 +127,19 @@ extern "C" int ubs_unpack_records(int64_t N, int D, const float *records, float 
     UBS_CHECK_ARG(((uintptr_t)records & 15) == 0, "unpack_records: records must be 16-byte aligned");
     PackSegs segs{{mean, rgb, opacity, beta0, beta_c, scale, l_triangle}};
     return launch_pack<false>(N, D, segs, const_cast<float *>(records), (cudaStream_t)stream);
+}
+
+extern "C" int ubs_pack_gradient_rows(int64_t CN, const float *v_means2d, const float *v_depths, const float *v_conics,
+                                      const float *v_opacities, const float *v_betas, const float *v_colors,
+                                      float *v_rows, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(CN >= 0, "pack_gradient_rows: bad size");
+    if (CN == 0) return UBS_OK;
+    UBS_CHECK_ARG(v_means2d && v_conics && v_opacities && v_betas && v_rows, "pack_gradient_rows: null pointer");
+    UBS_CHECK_ARG(((uintptr_t)v_rows & 15) == 0, "pack_gradient_rows: v_rows must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    pack_gradient_rows_kernel<<<(unsigned)ceil_div(CN, (int64_t)256), 256, 0, s>>>(
+        CN, v_means2d, v_depths, v_conics, v_opacities, v_betas, v_colors, (float4 *)v_rows);
+    UBS_LAUNCH_CHECK("pack_gradient_rows_kernel");
+    return UBS_OK;
 }

@@ -52,7 +52,8 @@ SIGNATURES = {
                                       c_float, c_float, c_int, c_int, c_int, c_int] + [_P] * 12 +
                               [c_size_t, c_int, _P, _P]),
     "ubs_fused_project_bwd": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_int] +
-                              [_P] * 10 + [c_int, _P, _P, _P]),
+                              [_P, _P, _P, c_int, _P] + [c_int, _P, _P, _P]),
+    "ubs_pack_gradient_rows": (c_int, [c_int64] + [_P] * 8),
     "ubs_pack_records": (c_int, [c_int64, c_int] + [_P] * 9),
     "ubs_unpack_records": (c_int, [c_int64, c_int] + [_P] * 9),
     "ubs_l1_ssim_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
@@ -61,9 +62,10 @@ SIGNATURES = {
     "ubs_adam_step": (c_int, [c_int64, c_int, c_int64, c_int64, _P, _P, _P, _P, _P, c_double, c_double, c_double, c_int64, c_double,
                               c_double, _P]),
     "ubs_fused_project_bwd_adam": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_int] +
-                                   [_P] * 12 + [c_double, c_double, c_double, c_int64, c_double, c_double, _P, _P]),
+                                   [_P, _P, _P, c_int, _P, _P, _P] +
+                                   [c_double, c_double, c_double, c_int64, c_double, c_double, _P, _P]),
     "ubs_fused_project_bwd_scatter": (c_int, [c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_int] +
-                                      [_P] * 9 + [c_int, c_int, c_int64, _P, _P, _P]),
+                                      [_P, _P, _P, c_int] + [c_int, c_int, c_int64, _P, _P, _P]),
     "ubs_reduce_adam_gather": (c_int, [c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P, c_double, c_double,
                                        c_double, c_int64, c_double, c_double, _P]),
     "ubs_mcmc_relocate": (c_int, [c_int64, c_int, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P]),

@@ -273,11 +273,12 @@ class FusedRasterizer:
     def _grad_buffers(self):
         """Screen-space gradient storage of the frame's mode, to be zeroed before the compositing backward.
         RGB frames: one 48-byte row per (camera, primitive), v_rows [C, N, 12] (ubs_rasterize_bwd_rows; layout in
-        include/ubs_b200.h).  Depth modes (and grad_rows=False): the separate arrays of ubs_rasterize_bwd_splats."""
+        include/ubs_b200.h).  Depth modes (and grad_rows=False): the separate arrays of ubs_rasterize_bwd_splats,
+        which composite_backward() then packs into v_rows (the projection backward reads rows only)."""
         C, N = self.C, self.N
+        if getattr(self, "v_rows", None) is None:
+            self.v_rows = torch.empty((C, N, 12), dtype=torch.float32, device=self.device)
         if self.channels == 3 and self.grad_rows:
-            if getattr(self, "v_rows", None) is None:
-                self.v_rows = torch.empty((C, N, 12), dtype=torch.float32, device=self.device)
             return self.v_rows
         if getattr(self, "_gflat", None) is None:
             self._gflat = torch.empty((C * N * 11,), dtype=torch.float32, device=self.device)
@@ -291,15 +292,10 @@ class FusedRasterizer:
         return self._gflat if self.channels != 3 else self._gflat[:self.C * self.N * 10]
 
     def grad_args(self, sl: Optional[slice] = None):
-        """The seven gradient-input pointers of ubs_fused_project_bwd* (v_means2d, v_depths, v_conics, v_opacities,
-        v_betas, v_colors, v_rows) for the frame composite_backward() last differentiated; sl = a row range.  The
-        pointers address buffers owned by self (row slices are views at an offset, no temporaries)."""
-        sl = slice(None) if sl is None else sl
-        if self.channels == 3 and self.grad_rows:
-            return (None, None, None, None, None, None, ptr(self.v_rows[:, sl]))
-        return (ptr(self.v_means2d[:, sl]), ptr(self.v_depths[:, sl]) if self.channels != 3 else None,
-                ptr(self.v_conics[:, sl]), ptr(self.v_opacities[:, sl]), ptr(self.v_betas[:, sl]),
-                ptr(self.v_colors[:, sl]), None)
+        """(v_rows, rows_form) of ubs_fused_project_bwd* for the frame composite_backward() last differentiated;
+        sl = a row range (a view at an offset of a buffer owned by self, no temporary)."""
+        rows = self.v_rows if sl is None else self.v_rows[:, sl]
+        return ptr(rows), (1 if self.channels == 3 and self.grad_rows else 0)
 
     @torch.no_grad()
     def backward(self, records: Tensor, viewmats: Tensor, Ks: Tensor, cam_pos: Tensor, timestamps: Optional[Tensor],
@@ -362,6 +358,10 @@ class FusedRasterizer:
               ptr(v_rc), ptr(v_ra), ptr(self.v_means2d), ptr(self.v_conics), ptr(self.v_colors),
               ptr(self.v_opacities), ptr(self.v_betas), ptr(self.v_depths) if ch != 3 else None, s),
               "ubs_rasterize_bwd_splats")
+            check(lib.ubs_pack_gradient_rows(
+              C * N, ptr(self.v_means2d), ptr(self.v_depths) if ch != 3 else None, ptr(self.v_conics),
+              ptr(self.v_opacities), ptr(self.v_betas), ptr(self.v_colors), ptr(self.v_rows), s),
+              "ubs_pack_gradient_rows")
 
     @torch.no_grad()
     def project_backward_rows(self, records, viewmats, Ks, cam_pos, timestamps, v_records, begin: int, count: int,
