@@ -481,6 +481,15 @@ def run_ours(args, rank, local_rank, world):
     ms_full, launches_full, clocks_full, stages_full = timed(train_full, args.steps, args.warmup, True)
     its_full = world * args.steps / (ms_full / 1e3)
     used_sharded = sharded is not None
+    scatter_full = None
+    if sharded is not None and sharded.exchange == "pull":
+        # the earlier form of the sharded step, for comparison: 144/176-byte gradient-record tiles pushed into the
+        # owners' staging buffers, owner-side reduce + Adam + parameter stores
+        sharded.exchange = "scatter"
+        ms_s, _, _, st_s = timed(train_full, args.steps, args.warmup, True)
+        scatter_full = {"value": world * args.steps / (ms_s / 1e3), "unit": "it/s", "ms_per_step": ms_s / args.steps,
+                        "stages_ms": {k: v[1] for k, v in st_s.items()}}
+        sharded.exchange = "pull"
     del rec_train, tstep
     nccl_full = None
     paths_check = None
@@ -689,10 +698,11 @@ def run_ours(args, rank, local_rank, world):
                        "stages_ms": {k: v[1] for k, v in stages_full.items()},
                        "update": ("Adam inside the projection-backward kernel" if world == 1 else
                                   "chunk-pipelined NCCL all-reduce + Adam on every rank" if not used_sharded else
-                                  "rows sharded over the ranks: NVLink peer stores from the projection-backward "
-                                  "kernel into the owner's staging buffer, owner-side reduce + Adam + parameter "
-                                  "stores to every rank (symmetric memory)"),
-                       "nccl_allreduce_path": nccl_full},
+                                  "rows sharded over the ranks (symmetric memory): every rank leaves its view's 48-byte "
+                                  "screen-space gradient rows in a peer-mapped buffer; the owner of a shard pulls all "
+                                  "views' rows of its primitives by bulk copies over NVLink inside ONE kernel that runs "
+                                  "the projection backward over the views, Adam, and stores the new rows to every rank"),
+                       "nccl_allreduce_path": nccl_full, "sharded_scatter_path": scatter_full},
         "roofline": roofline, "stages": stage_roof, "stages_ms": {k: v[1] for k, v in stages.items()},
         "work": counts, "cpu_baseline": cpu,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -704,6 +714,7 @@ def run_ours(args, rank, local_rank, world):
         "train_full_summary": {"value": its_full, "unit": "it/s", "ms_per_step": ms_full / args.steps,
                                "stages_ms": {k: round(v[1], 4) for k, v in stages_full.items()},
                                "nccl_path_it_per_s": None if nccl_full is None else nccl_full["value"],
+                               "scatter_path_it_per_s": None if scatter_full is None else scatter_full["value"],
                                "paths_check": paths_check},
         "reference_cuda": ref_cuda_line, "dropin": dropin_line,
     }

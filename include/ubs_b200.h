@@ -232,7 +232,10 @@ int ubs_rasterize_bwd_rows(int C, int64_t N, const int64_t *n_isects, int64_t is
                            const float *backgrounds, const uint8_t *masks, int width, int height, int tile_size,
                            const int32_t *offsets, const int32_t *flatten_ids, const float *render_alphas,
                            const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
-                           float *v_rows, void *stream);
+                           float *v_rows,
+                           const int32_t *skip_flag, /* NULL, or the `status` of the frame's tile-list build: a
+                                                        truncated frame leaves v_rows untouched (zero gradient) */
+                           void *stream);
 /* Rows for ubs_fused_project_bwd* (rows_form = 0) from the separate gradient arrays of ubs_rasterize_bwd[_splats]:
  * 0..2 v_colors | 3..5 v_conics | 6, 7 v_means2d | 8 v_opacities | 9 v_betas | 10 v_depths | 11 zero.
  * v_colors / v_depths may be NULL (zeros).  CN = C * N.                                                          */
@@ -372,6 +375,21 @@ int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *records, const 
                                   int world, int rank, int64_t shard_rows, float *const *h_staging,
                                   const int32_t *skip_flag, /* as in ubs_fused_project_bwd: zero tiles are sent */
                                   void *stream);
+/* Pull form of the sharded step (the default): what crosses NVLink before the update are the 48-byte screen-space
+ * gradient rows, not the 144/176-byte parameter gradients.  Every rank renders its own view and leaves its rows
+ * (ubs_rasterize_bwd_rows, with skip_flag) in a peer-mapped [N,12] buffer; after a barrier the owner of a shard runs
+ * this: per 128-row tile, the rows of all `world` views arrive by bulk copies from the ranks' buffers, the projection
+ * backward sums the views' gradients in registers (camera c = rank c's view: viewmats [world,4,4], Ks [world,3,3],
+ * cam_pos [world,3], timestamps [world]), Adam is applied (moments [shard_rows, stride], local) and the new record
+ * tile is stored into every rank's records.  A barrier follows.  Equal to ubs_fused_project_bwd_adam over the
+ * world-camera batch, restricted to the shard.                                                                      */
+int ubs_fused_project_bwd_adam_pull(int64_t N, int D, int world, int rank, int64_t shard_rows,
+                                    float *const *h_peer_records, const float *const *h_peer_rows,
+                                    const float *viewmats, const float *Ks, const float *cam_pos,
+                                    const float *timestamps, int width, int height, float eps2d,
+                                    int calc_compensations, float *exp_avg_shard, float *exp_avg_sq_shard,
+                                    const double *h_lr, double beta1, double beta2, double eps, int64_t step,
+                                    double opacity_reg, double scale_reg, void *stream);
 int ubs_reduce_adam_gather(int64_t N, int D, int world, int rank, int64_t shard_rows, const float *staging,
                            float *exp_avg_shard, float *exp_avg_sq_shard, float *const *h_peer_records,
                            float *mc_records, /* NULL, or the NVLS multicast address of the records buffers: one

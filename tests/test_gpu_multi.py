@@ -29,23 +29,31 @@ rz = fused.FusedRasterizer(D, N, W, H, n_cams=1)
 # (a) NCCL path: chunk-pipelined all-reduce + Adam on every rank
 rec_a = rec0.clone()
 ts_a = training.TrainStep(rz, training.PackedAdam(D, N), world=world)
-# (b) sharded P2P path
+# (b) sharded step, pull form (default): the owners read the views' 48-byte gradient rows from their peers
 st = parallel.ShardedState.create(D, N)
+assert st.exchange == "pull"
 st.records.copy_(rec0)
 ts_b = training.TrainStep(rz, training.PackedAdam(D, N, allocate_moments=False), world=world, sharded=st)
+# (c) sharded step, scatter form: gradient-record tiles pushed into the owners' staging buffers
+st_c = parallel.ShardedState.create(D, N)
+st_c.exchange = "scatter"
+st_c.records.copy_(rec0)
+ts_c = training.TrainStep(rz, training.PackedAdam(D, N, allocate_moments=False), world=world, sharded=st_c)
 for it in range(4):
     la = ts_a.step(rec_a, *args, gt, opacity_reg=0.01, scale_reg=0.01, batch_size=world)[2].item()
     lb = ts_b.step(st.records, *args, gt, opacity_reg=0.01, scale_reg=0.01, batch_size=world)[2].item()
-    assert abs(la - lb) < 1e-5, (it, la, lb)
+    lc = ts_c.step(st_c.records, *args, gt, opacity_reg=0.01, scale_reg=0.01, batch_size=world)[2].item()
+    assert abs(la - lb) < 1e-5 and abs(la - lc) < 1e-5, (it, la, lb, lc)
 torch.cuda.synchronize()
 # atomics in the compositing backward: rounding-level noise in the gradients, visible only where Adam divides ~0 by ~0
-bad = ((rec_a - st.records).abs() > 1e-6).float().mean().item()
+bad = max(((rec_a - s.records).abs() > 1e-6).float().mean().item() for s in (st, st_c))
 assert bad < 1e-3, bad
 # every rank holds the same parameters
-mine = st.records.clone()
-other = [torch.empty_like(mine) for _ in range(world)]
-dist.all_gather(other, mine)
-assert all(torch.equal(o, other[0]) for o in other)
+for s in (st, st_c):
+    mine = s.records.clone()
+    other = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(other, mine)
+    assert all(torch.equal(o, other[0]) for o in other)
 dist.destroy_process_group()
 print("rank", rank, "ok", bad)
 '''

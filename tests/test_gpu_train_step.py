@@ -439,3 +439,68 @@ def test_sharded_step_kernels_equal_allreduce_then_adam_bitwise(world, D, N):
             assert torch.equal(st.exp_avg[:n], ref_adam.exp_avg[b:b + n]), (it, r)
             assert torch.equal(st.exp_avg_sq[:n], ref_adam.exp_avg_sq[b:b + n]), (it, r)
             assert float(st.exp_avg[n:].abs().sum()) == 0.0  # padding rows of the last shard never move
+
+
+@pytest.mark.parametrize("world,D,N", [(4, 6, 30011), (2, 7, 20000), (8, 6, 9000)])
+def test_sharded_pull_step_equals_the_multi_camera_fused_update(world, D, N):
+    """Pull form of the sharded step (every rank leaves its view's 48-byte gradient rows in a buffer its peers can read;
+    the owner of a shard fetches all views' rows of its primitives, runs projection backward + Adam on them and stores
+    the new rows into every rank's records), all ranks simulated in ONE process on ordinary tensors, against the
+    single-GPU ubs_fused_project_bwd_adam over the same `world` views as one batch, fed the same gradient rows.
+    The owner recomputes each view's conic instead of reading the forward's array and tells visibility from the row
+    being non-zero; parameters and moments must agree to rounding on every rank."""
+    import ctypes
+
+    from ubs_b200 import fused, parallel, synth, training
+    from ubs_b200._lib import check, ptr
+
+    W, H = 256, 192
+    scene = synth.make_scene(N, D, seed=50 + world).to("cuda")
+    cams = synth.make_cameras(world, W, H, seed=9, timestamps=[0.1 * (k + 1) for k in range(world)], device="cuda")
+    vm, K, cp = (torch.stack([getattr(c, k) for c in cams]).contiguous() for k in ("viewmat", "K", "cam_pos"))
+    ts = torch.tensor([c.timestamp for c in cams], device="cuda") if D == 7 else None
+    bg = torch.rand(world, 3, device="cuda")
+    rec0 = fused.pack_records(D, *scene.tensors())
+    states = parallel.ShardedState.create_local_group(D, N, world)
+    rzs = [fused.FusedRasterizer(D, N, W, H, n_cams=1) for _ in range(world)]
+    for st, rz in zip(states, rzs):
+        st.records.copy_(rec0)
+        assert st.exchange == "pull"
+        st.attach(rz)
+    rz_ref = fused.FusedRasterizer(D, N, W, H, n_cams=world)
+    ref_rec, ref_adam = rec0.clone(), training.PackedAdam(D, N)
+    adams = [training.PackedAdam(D, N, allocate_moments=False) for _ in range(world)]
+    g = torch.Generator(device="cuda").manual_seed(4)
+    s = torch.cuda.current_stream().cuda_stream
+    bitwise = True
+    for it in range(3):
+        for r, (st, rz) in enumerate(zip(states, rzs)):
+            one = (vm[r:r + 1], K[r:r + 1], cp[r:r + 1], None if ts is None else ts[r:r + 1])
+            rz.forward(st.records, *one, bg[r:r + 1])
+            v_rc = torch.randn(1, H, W, 3, device="cuda", generator=g) / (W * H)
+            rz.composite_backward(bg[r:r + 1], v_rc, torch.zeros(1, H, W, 1, device="cuda"))
+            assert rz.v_rows.data_ptr() == st.rows.data_ptr() and float(st.rows.abs().sum()) > 0
+        # reference: the world views as ONE batch on one GPU, same rows
+        rz_ref.forward(ref_rec, vm, K, cp, ts, bg)
+        rows_all = torch.cat([st.rows for st in states]).contiguous()
+        ref_adam.step_count += 1
+        cols = (ctypes.c_double * ref_adam.stride)(*ref_adam.lr_columns())
+        check(rz_ref.lib.ubs_fused_project_bwd_adam(
+            world, N, D, ptr(ref_rec), ptr(vm), ptr(K), ptr(cp), ptr(ts), W, H, rz_ref.eps2d, 0, ptr(rz_ref.radii),
+            ptr(rz_ref.conics), ptr(rows_all), 1, ptr(ref_adam.exp_avg), ptr(ref_adam.exp_avg_sq),
+            ctypes.cast(cols, ctypes.c_void_p), 0.9, 0.999, 1e-15, ref_adam.step_count, 0.01, 0.02, None, s),
+            "ubs_fused_project_bwd_adam")
+        for r, (st, rz) in enumerate(zip(states, rzs)):
+            parallel.sharded_pull_update(rz, st, adams[r], vm, K, cp, ts, 0.01, 0.02)
+        for r, st in enumerate(states):
+            bitwise &= torch.equal(st.records, ref_rec)
+            assert torch.equal(st.records, states[0].records), (it, r)  # replicas stay identical
+            # Adam's first steps move every touched parameter by ~lr whatever the gradient's size: compare in units of
+            # the largest step taken
+            step = (ref_rec - rec0).abs().max().item()
+            assert (st.records - ref_rec).abs().max().item() <= 2e-3 * step, (it, r)
+            b, n = st.my_rows()
+            scale = ref_adam.exp_avg.abs().max().item()
+            assert (st.exp_avg[:n] - ref_adam.exp_avg[b:b + n]).abs().max().item() <= 1e-5 * scale, (it, r)
+            assert float(st.exp_avg[n:].abs().sum()) == 0.0  # padding rows of the last shard never move
+    print("pull form bit-identical to the batched single-GPU update:", bitwise)

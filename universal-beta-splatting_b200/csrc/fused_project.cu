@@ -9,6 +9,8 @@
 // global memory, fetched with ONE TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx) into shared memory;
 // threads then read their own record with conflict-free 128-bit shared loads (row strides of 36 / 44 floats map
 // each quarter-warp onto 32 distinct banks).
+#include <algorithm>
+
 #include "common.cuh"
 #include "cond_math.cuh"
 #include "isect.cuh"
@@ -260,7 +262,16 @@ struct ScatterDst {
     int rank;
 };
 
-// Options shared by the three entry points of the backward kernel.
+// Sharded train step, pull form: the owner of a shard of rows reads every rank's screen-space gradient rows of that shard
+// straight from the ranks' (peer-mapped) v_rows buffers and stores the updated parameter tiles into every rank's records.
+struct PullSrc {
+    const float *rows[UBS_MAX_RANKS];  // rows[c] = rank c's [N, 12] gradient rows (camera c of the step)
+    float *records[UBS_MAX_RANKS];     // records[g] = rank g's [N, stride] parameters
+    int world;
+    int64_t row0;                      // first row of this rank's shard
+};
+
+// Options shared by the entry points of the backward kernel.
 struct BwdOpts {
     int activated;             // records hold activated values (see decode_record): no activation derivative
     const float *query;        // NULL, or [N, D-3] queries given by the caller instead of the view direction
@@ -268,6 +279,17 @@ struct BwdOpts {
     const float *v_rows;       // [C, N, 12] screen-space gradient rows (layout: include/ubs_b200.h)
     int moment_form;           // rows of ubs_rasterize_bwd_rows (1) or of ubs_pack_gradient_rows (0)
 };
+
+// a 48-byte gradient row with all ten gradient slots +-0: the primitive received nothing from that view
+__device__ __forceinline__ bool pull_row_nonzero(const float *row) {
+    const float4 *r = reinterpret_cast<const float4 *>(row);
+    const float4 a = r[0], b = r[1];
+    const float2 c = *reinterpret_cast<const float2 *>(row + 8);
+    const uint32_t bits = __float_as_uint(a.x) | __float_as_uint(a.y) | __float_as_uint(a.z) | __float_as_uint(a.w) |
+                          __float_as_uint(b.x) | __float_as_uint(b.y) | __float_as_uint(b.z) | __float_as_uint(b.w) |
+                          __float_as_uint(c.x) | __float_as_uint(c.y);
+    return (bits << 1) != 0u;
+}
 
 // Backward of fused_project_fwd_kernel: one thread per primitive, looping over cameras, so the per-primitive sums
 // need no atomics.  Recomputes the cheap forward intermediates from the record instead of storing them.
@@ -277,7 +299,13 @@ struct BwdOpts {
 // gradient computation; every thread then applies torch.optim.Adam to its own row straight from the gradient in
 // its registers and the updated parameters and moments go back with three bulk stores.  The gradient records are
 // never written: 6 record-sized HBM streams instead of the 2 + 7 of backward-then-optimiser.
-template <int D, int MINB, bool ADAM>
+//
+// PULL = true (with ADAM; sharded train step): the "cameras" are the `world` ranks' views, N counts the rows of this
+// rank's shard, `records_in` / the moments point at the shard; the gradient rows of the CTA's 128 primitives are fetched
+// from every rank's v_rows with one bulk copy per rank (6 KB each, over NVLink) next to the record and moment tiles;
+// visibility is "the row is non-zero", the conic is recomputed (the forward outputs of the other ranks' cameras are not
+// here), and the updated record tile goes to every rank with one bulk store each.
+template <int D, int MINB, bool ADAM, bool PULL = false>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
 fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in, const float *__restrict__ viewmats,
                          const float *__restrict__ Ks, const float *__restrict__ cam_pos,
@@ -285,7 +313,8 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
                          int calc_comp, const int32_t *__restrict__ radii, const float *__restrict__ conics,
                          float *__restrict__ v_records, float *__restrict__ exp_avg,
                          float *__restrict__ exp_avg_sq, const AdamParams adam, const ScatterDst scatter,
-                         const BwdOpts opts) {
+                         const BwdOpts opts, const PullSrc pull) {
+    static_assert(!PULL || ADAM, "the pull form updates the parameters");
     constexpr int Cd = D - 3, M = NdDims<D>::M;
     // the frame this gradient belongs to lost pairs to the capacity bound (isect.cuh: report_truncation): with ADAM the
     // update is not applied at all, otherwise the view contributes a zero gradient (it is dropped from the batch)
@@ -297,6 +326,7 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
     float *const s_rec = s_tiles;
     float *const s_m = s_tiles + kFusedThreads * STRIDE;
     float *const s_v = s_tiles + 2 * kFusedThreads * STRIDE;
+    float *const s_rows = s_tiles + 3 * kFusedThreads * STRIDE;  // PULL: [world][128][12] gradient rows
     __shared__ __align__(8) uint64_t s_bar, s_bar2;
     const float *records = records_in;
 
@@ -309,8 +339,13 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(&s_bar, bytes);
+        const uint32_t row_bytes = (uint32_t)n_here * 12u * sizeof(float);
+        mbar_expect_tx(&s_bar, PULL ? bytes + (uint32_t)C * row_bytes : bytes);
         tma_bulk_g2s(s_rec, records + base * STRIDE, bytes, &s_bar);
+        if constexpr (PULL) {
+            for (int c = 0; c < C; ++c)
+                tma_bulk_g2s(s_rows + c * kFusedThreads * 12, pull.rows[c] + (pull.row0 + base) * 12, row_bytes, &s_bar);
+        }
         if constexpr (ADAM) {
             mbar_expect_tx(&s_bar2, 2 * bytes);
             tma_bulk_g2s(s_m, exp_avg + base * STRIDE, bytes, &s_bar2);
@@ -326,7 +361,13 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
     int my_row = -1, any_row = -1;
     {
         bool vis = false;
-        if (threadIdx.x < n_here) {
+        if constexpr (PULL) {
+            mbar_wait(&s_bar, 0);  // records and gradient rows have landed
+            if (threadIdx.x < n_here) {
+                for (int cid = 0; cid < C && !vis; ++cid)
+                    vis = pull_row_nonzero(s_rows + (cid * kFusedThreads + threadIdx.x) * 12);
+            }
+        } else if (threadIdx.x < n_here) {
             int cid = 0;
             for (; cid < C && !vis && !skip; ++cid) vis = radii[(int64_t)cid * N + base + threadIdx.x] > 0;
             if (vis) {
@@ -359,7 +400,7 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
         if ((int)threadIdx.x < n_vis) my_row = s_row[threadIdx.x];
         if (ADAM && (int)threadIdx.x < n_here) any_row = s_row[threadIdx.x];
     }
-    mbar_wait(&s_bar, 0);  // the records have landed (the visibility loads above overlapped the bulk copy)
+    if constexpr (!PULL) mbar_wait(&s_bar, 0);  // the records have landed (the visibility loads above overlapped the bulk copy)
     const int64_t gid = base + my_row;
     const bool active = my_row >= 0;
     float grad[STRIDE];
@@ -423,7 +464,13 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
 
         for (int cid = 0; cid < C; ++cid) {
             const int64_t idx = (int64_t)cid * N + gid;
-            if (radii[idx] <= 0) continue;
+            const float4 *row = PULL ? reinterpret_cast<const float4 *>(s_rows + (cid * kFusedThreads + my_row) * 12)
+                                     : reinterpret_cast<const float4 *>(opts.v_rows + idx * 12);
+            if constexpr (PULL) {
+                if (!pull_row_nonzero(reinterpret_cast<const float *>(row))) continue;
+            } else {
+                if (radii[idx] <= 0) continue;
+            }
             const Cam cam = load_cam(viewmats + cid * 16, Ks + cid * 9);
             float x[Cd];
             if (opts.query != nullptr) {
@@ -445,10 +492,17 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
             float mean[3], o_cond;
             cond_apply<Cd>(prep, xyz, x, o_in, beta_c, mean, o_cond);
 
-            const float conic[3] = {conics[idx * 3], conics[idx * 3 + 1], conics[idx * 3 + 2]};
+            float conic[3], comp = 0.f;
+            if constexpr (PULL) {
+                // the conic of the forward pass, recomputed (same function, same inputs as fused_project_fwd_kernel)
+                const Splat2D f = project_splat(cam, mean, s6, width, height, eps2d, -3.0e38f, 3.0e38f, -1.f);
+                conic[0] = f.conic[0], conic[1] = f.conic[1], conic[2] = f.conic[2];
+                comp = f.compensation;
+            } else {
+                conic[0] = conics[idx * 3], conic[1] = conics[idx * 3 + 1], conic[2] = conics[idx * 3 + 2];
+            }
             // one 48-byte gradient row; the two forms differ in three slots (selects, no branch: the code below is the
             // same in every instantiation, which keeps the ADAM and plain kernels bit-identical)
-            const float4 *row = reinterpret_cast<const float4 *>(opts.v_rows + idx * 12);
             const float4 q0 = row[0], q1 = row[1], q2 = row[2];
             const bool moment = opts.moment_form != 0;
             const float v_col[3] = {q0.x, q0.y, q0.z};
@@ -458,10 +512,12 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
                                  moment ? __fmaf_rn(b2, q1.z, __fmul_rn(c2, q1.w)) : q1.w};
             float v_o = q2.x;
             const float v_b = moment ? __fmul_rn(q2.y, 0.693147180559945f) : q2.y, v_d = q2.z;
-            float comp = 0.f, v_comp = 0.f;
+            float v_comp = 0.f;
             if (calc_comp) {
-                const Splat2D f = project_splat(cam, mean, s6, width, height, eps2d, -3.0e38f, 3.0e38f, -1.f);
-                comp = f.compensation;
+                if constexpr (!PULL) {
+                    const Splat2D f = project_splat(cam, mean, s6, width, height, eps2d, -3.0e38f, 3.0e38f, -1.f);
+                    comp = f.compensation;
+                }
                 v_comp = v_o * o_cond;
                 v_o = v_o * comp;
             }
@@ -525,7 +581,7 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
     if constexpr (ADAM) {
         mbar_wait(&s_bar2, 0);  // the moment tiles landed long ago
         if (any_row >= 0) {
-            const int64_t row = base + any_row;
+            const int64_t row = (PULL ? pull.row0 : 0) + base + any_row;
             float4 *p4 = reinterpret_cast<float4 *>(s_rec + any_row * STRIDE);
             float4 *m4 = reinterpret_cast<float4 *>(s_m + any_row * STRIDE);
             float4 *v4 = reinterpret_cast<float4 *>(s_v + any_row * STRIDE);
@@ -561,7 +617,12 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (threadIdx.x == 0) {
-            tma_bulk_s2g_issue(const_cast<float *>(records_in) + base * STRIDE, s_rec, bytes);
+            if constexpr (PULL) {
+                for (int g = 0; g < pull.world; ++g)
+                    tma_bulk_s2g_issue(pull.records[g] + (pull.row0 + base) * STRIDE, s_rec, bytes);
+            } else {
+                tma_bulk_s2g_issue(const_cast<float *>(records_in) + base * STRIDE, s_rec, bytes);
+            }
             tma_bulk_s2g_issue(exp_avg + base * STRIDE, s_m, bytes);
             tma_bulk_s2g_issue(exp_avg_sq + base * STRIDE, s_v, bytes);
             tma_bulk_commit_wait();
@@ -685,12 +746,12 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_records,
-            nullptr, nullptr, unused, no_scatter, opts);
+            nullptr, nullptr, unused, no_scatter, opts, PullSrc{});
     else
         fused_project_bwd_kernel<7, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, v_records,
-            nullptr, nullptr, unused, no_scatter, opts);
+            nullptr, nullptr, unused, no_scatter, opts, PullSrc{});
     UBS_LAUNCH_CHECK("fused_project_bwd_kernel");
     return UBS_OK;
 }
@@ -725,7 +786,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
         fused_project_bwd_kernel<6, 3, true><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, nullptr,
-            exp_avg, exp_avg_sq, a, ScatterDst{}, opts);
+            exp_avg, exp_avg_sq, a, ScatterDst{}, opts, PullSrc{});
     } else {
         UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<7, 3, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -734,7 +795,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
         fused_project_bwd_kernel<7, 3, true><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, nullptr,
-            exp_avg, exp_avg_sq, a, ScatterDst{}, opts);
+            exp_avg, exp_avg_sq, a, ScatterDst{}, opts, PullSrc{});
     }
     UBS_LAUNCH_CHECK("fused_project_bwd_adam_kernel");
     return UBS_OK;
@@ -775,12 +836,70 @@ extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *reco
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             1, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, nullptr,
-            nullptr, nullptr, unused, sc, opts);
+            nullptr, nullptr, unused, sc, opts, PullSrc{});
     else
         fused_project_bwd_kernel<7, 3, false><<<gx, kFusedThreads, smem, s>>>(
             1, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
             calc_compensations, radii, conics, nullptr,
-            nullptr, nullptr, unused, sc, opts);
+            nullptr, nullptr, unused, sc, opts, PullSrc{});
     UBS_LAUNCH_CHECK("fused_project_bwd_scatter_kernel");
+    return UBS_OK;
+}
+
+extern "C" int ubs_fused_project_bwd_adam_pull(int64_t N, int D, int world, int rank, int64_t shard_rows,
+                                               float *const *h_peer_records, const float *const *h_peer_rows,
+                                               const float *viewmats, const float *Ks, const float *cam_pos,
+                                               const float *timestamps, int width, int height, float eps2d,
+                                               int calc_compensations, float *exp_avg_shard, float *exp_avg_sq_shard,
+                                               const double *h_lr, double beta1, double beta2, double eps, int64_t step,
+                                               double opacity_reg, double scale_reg, void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(N >= 0 && width > 0 && height > 0, "fused_project_bwd_adam_pull: bad sizes");
+    UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd_adam_pull: D must be 6 or 7 (got %d)", D);
+    UBS_CHECK_ARG(world >= 1 && world <= UBS_MAX_RANKS && rank >= 0 && rank < world,
+                  "fused_project_bwd_adam_pull: rank %d of %d (at most %d ranks)", rank, world, UBS_MAX_RANKS);
+    UBS_CHECK_ARG(shard_rows > 0 && shard_rows % kFusedThreads == 0 && shard_rows * world >= N,
+                  "fused_project_bwd_adam_pull: shard_rows must be a positive multiple of %d covering N", kFusedThreads);
+    UBS_CHECK_ARG(step >= 1, "fused_project_bwd_adam_pull: step counts from 1 (got %lld)", (long long)step);
+    const int64_t row0 = (int64_t)rank * shard_rows;
+    const int64_t count = std::max<int64_t>(0, std::min<int64_t>(shard_rows, N - row0));
+    if (count == 0) return UBS_OK;
+    UBS_CHECK_ARG(h_peer_records && h_peer_rows && viewmats && Ks && cam_pos && exp_avg_shard && exp_avg_sq_shard && h_lr,
+                  "fused_project_bwd_adam_pull: null pointer");
+    UBS_CHECK_ARG(D != 7 || timestamps != nullptr, "fused_project_bwd_adam_pull: D=7 needs timestamps");
+    PullSrc pull{};
+    for (int g = 0; g < world; ++g) {
+        UBS_CHECK_ARG(h_peer_records[g] && h_peer_rows[g] &&
+                          ((((uintptr_t)h_peer_records[g]) | ((uintptr_t)h_peer_rows[g])) & 15) == 0,
+                      "fused_project_bwd_adam_pull: records / rows of rank %d null or not 16-byte aligned", g);
+        pull.records[g] = h_peer_records[g];
+        pull.rows[g] = h_peer_rows[g];
+    }
+    UBS_CHECK_ARG((((uintptr_t)exp_avg_shard | (uintptr_t)exp_avg_sq_shard) & 15) == 0,
+                  "fused_project_bwd_adam_pull: moments must be 16-byte aligned");
+    pull.world = world;
+    pull.row0 = row0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned gx = (unsigned)ceil_div(count, kFusedThreads);
+    const int stride = UBS_RECORD_STRIDE(D);
+    const size_t smem = ((size_t)3 * kFusedThreads * stride + (size_t)world * kFusedThreads * 12) * sizeof(float);
+    const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
+    const BwdOpts opts{0, nullptr, nullptr, nullptr, 1};
+    const float *records = pull.records[rank] + row0 * stride;
+#define UBS_PULL_LAUNCH(DD)                                                                                            \
+    do {                                                                                                               \
+        UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<DD, 2, true, true>,                                 \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<DD, 2, true, true>,                                 \
+                                          cudaFuncAttributePreferredSharedMemoryCarveout, 100));                       \
+        fused_project_bwd_kernel<DD, 2, true, true><<<gx, kFusedThreads, smem, s>>>(                                   \
+            world, count, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,        \
+            calc_compensations, nullptr, nullptr, nullptr, exp_avg_shard, exp_avg_sq_shard, a, ScatterDst{}, opts,     \
+            pull);                                                                                                     \
+    } while (0)
+    if (D == 6) UBS_PULL_LAUNCH(6);
+    else UBS_PULL_LAUNCH(7);
+#undef UBS_PULL_LAUNCH
+    UBS_LAUNCH_CHECK("fused_project_bwd_adam_pull_kernel");
     return UBS_OK;
 }

@@ -712,7 +712,10 @@ rasterize_bwd3_pairlane_kernel(int C, int64_t N, const int64_t *__restrict__ n_i
                                const float *__restrict__ v_render_alphas, float *__restrict__ v_means2d,
                                float *__restrict__ v_conics, float *__restrict__ v_colors,
                                float *__restrict__ v_opacities, float *__restrict__ v_betas,
-                               const float4 *__restrict__ splats, bool splat_colors, float *__restrict__ v_rows) {
+                               const float4 *__restrict__ splats, bool splat_colors, float *__restrict__ v_rows,
+                               const int32_t *__restrict__ skip_flag) {
+    // the frame lost pairs to the capacity bound (isect.cuh: report_truncation): it contributes no gradient
+    if (skip_flag != nullptr && *skip_flag != 0) return;
     const uint32_t cam = blockIdx.z;
     const uint32_t tile_id = blockIdx.y * tile_width + blockIdx.x;
     const uint32_t tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
@@ -920,7 +923,7 @@ int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
                 C, N, n_isects, cap, (const float2 *)means2d, conics, colors, opacities, betas, backgrounds, masks,
                 (uint32_t)width, (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids,
                 v_render_colors, v_render_alphas, v_means2d, v_conics, v_colors, v_opacities, v_betas,
-                (const float4 *)splats, splat_colors != 0, nullptr);
+                (const float4 *)splats, splat_colors != 0, nullptr, nullptr);
             UBS_LAUNCH_CHECK("rasterize_bwd_kernel");
             return UBS_OK;
         }
@@ -944,7 +947,8 @@ int launch_bwd(int C, int64_t N, const int64_t *n_isects, int64_t cap, const flo
 int launch_bwd_rows(int C, int64_t N, const int64_t *n_isects, int64_t cap, const float *splats,
                     const float *backgrounds, const uint8_t *masks, int width, int height, const int32_t *offsets,
                     const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
-                    const float *v_render_colors, const float *v_render_alphas, float *v_rows, cudaStream_t s) {
+                    const float *v_render_colors, const float *v_render_alphas, float *v_rows, const int32_t *skip_flag,
+                    cudaStream_t s) {
     const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
     dim3 grid(tw, th, (unsigned)C), block(kTilePixels, 1, 1);
     // four pixels in flight per lane at 3 CTAs / SM measured faster than two at 4 CTAs / SM (1.124 against 1.156 ms, cfg3)
@@ -952,7 +956,7 @@ int launch_bwd_rows(int C, int64_t N, const int64_t *n_isects, int64_t cap, cons
     kern<<<grid, block, 0, s>>>(
         C, N, n_isects, cap, nullptr, nullptr, nullptr, nullptr, nullptr, backgrounds, masks, (uint32_t)width,
         (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas,
-        nullptr, nullptr, nullptr, nullptr, nullptr, (const float4 *)splats, true, v_rows);
+        nullptr, nullptr, nullptr, nullptr, nullptr, (const float4 *)splats, true, v_rows, skip_flag);
     UBS_LAUNCH_CHECK("rasterize_bwd_rows_kernel");
     return UBS_OK;
 }
@@ -1038,7 +1042,7 @@ extern "C" int ubs_rasterize_bwd_rows(int C, int64_t N, const int64_t *n_isects,
                                       int height, int tile_size, const int32_t *offsets, const int32_t *flatten_ids,
                                       const float *render_alphas, const int32_t *last_ids,
                                       const float *v_render_colors, const float *v_render_alphas, float *v_rows,
-                                      void *stream) {
+                                      const int32_t *skip_flag, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "rasterize_bwd_rows: bad sizes");
     UBS_CHECK_ARG(tile_size == kTile, "rasterize_bwd_rows: tile_size must be %d (got %d)", kTile, tile_size);
@@ -1049,5 +1053,5 @@ extern "C" int ubs_rasterize_bwd_rows(int C, int64_t N, const int64_t *n_isects,
     UBS_CHECK_ARG((((uintptr_t)splats | (uintptr_t)v_rows) & 15) == 0,
                   "rasterize_bwd_rows: splats / v_rows must be 16-byte aligned");
     return launch_bwd_rows(C, N, n_isects, isect_capacity, splats, backgrounds, masks, width, height, offsets, flatten_ids,
-                           render_alphas, last_ids, v_render_colors, v_render_alphas, v_rows, (cudaStream_t)stream);
+                           render_alphas, last_ids, v_render_colors, v_render_alphas, v_rows, skip_flag, (cudaStream_t)stream);
 }

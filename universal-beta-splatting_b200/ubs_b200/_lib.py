@@ -44,7 +44,10 @@ SIGNATURES = {
                                          _P, _P, _P]),
     "ubs_rasterize_bwd_splats": (c_int, [c_int, c_int64, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_int] +
                                  [_P] * 13),
-    "ubs_rasterize_bwd_rows": (c_int, [c_int, c_int64, _P, c_int64, _P, _P, _P, c_int, c_int, c_int] + [_P] * 8),
+    "ubs_rasterize_bwd_rows": (c_int, [c_int, c_int64, _P, c_int64, _P, _P, _P, c_int, c_int, c_int] + [_P] * 9),
+    "ubs_fused_project_bwd_adam_pull": (c_int, [c_int64, c_int, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_int,
+                                                c_float, c_int, _P, _P, _P, c_double, c_double, c_double, c_int64,
+                                                c_double, c_double, _P]),
     "ubs_rasterize_bwd": (c_int, [c_int, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int] +
                           [_P] * 12),
     "ubs_rasterize_count": (c_int, [c_int, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),

@@ -89,6 +89,7 @@ class FusedRasterizer:
                  antialiased=False, sort_mode: str = "bin", on_overflow: str = "warn", grad_rows: bool = True):
         self.lib = _lib.load()
         self.grad_rows = grad_rows  # RGB frames: screen-space gradients as 48-byte rows (False: separate arrays)
+        self.v_rows = None          # [C, N, 12], allocated by the first backward (or attached by parallel.ShardedState)
         self.D, self.N, self.W, self.H, self.C = D, N, width, height, n_cams
         self.tile_size = tile_size
         self.tw, self.th = math.ceil(width / tile_size), math.ceil(height / tile_size)
@@ -350,7 +351,7 @@ class FusedRasterizer:
             check(lib.ubs_rasterize_bwd_rows(
               C, N, ptr(self.n_isects), self.capacity, ptr(self.splats), ptr(backgrounds), None, self.W, self.H,
               self.tile_size, ptr(self.offsets), ptr(self.flatten_ids), ptr(alphas), ptr(self.last_ids), ptr(v_rc),
-              ptr(v_ra), ptr(self.v_rows), s), "ubs_rasterize_bwd_rows")
+              ptr(v_ra), ptr(self.v_rows), ptr(self.status), s), "ubs_rasterize_bwd_rows")
           else:
             check(lib.ubs_rasterize_bwd_splats(
               C, N, ptr(self.n_isects), self.capacity, ptr(self.splats), None, ptr(backgrounds), None, ch, self.W,

@@ -91,7 +91,8 @@ class ShardedState:
     all ranks' states inside ONE process from ordinary tensors -- the kernels only see device addresses -- which is
     how the single-GPU tests exercise the multi-rank logic bit for bit."""
 
-    def __init__(self, D, N, world, rank, records_buf, staging_buf, peer_records, peer_staging, barrier):
+    def __init__(self, D, N, world, rank, records_buf, staging_buf, peer_records, peer_staging, barrier,
+                 rows_buf=None, peer_rows=None):
         from .fused import record_stride
 
         self.D, self.N, self.world, self.rank = D, N, world, rank
@@ -105,6 +106,17 @@ class ShardedState:
         self.exp_avg_sq = torch.zeros_like(self.exp_avg)
         self._barrier = barrier
         self.mc_records = None  # NVLS multicast address of the records buffers (set by create() when supported)
+        # pull form (default): this rank's [N, 12] screen-space gradient rows live in peer-mapped memory and the shard
+        # owners read them from there; "scatter": gradient-record tiles are pushed into the owners' staging buffers
+        self._rows_buf = rows_buf
+        self.rows = None if rows_buf is None else rows_buf[:N * 12].view(1, N, 12)
+        self.peer_rows = None if peer_rows is None else list(peer_rows)
+        self.exchange = "pull" if rows_buf is not None else "scatter"
+
+    def attach(self, rz):
+        """Make the rasteriser write its screen-space gradient rows into this state's peer-mapped buffer."""
+        assert rz.C == 1 and rz.N == self.N and rz.grad_rows and self.rows is not None
+        rz.v_rows = self.rows
 
     def barrier(self):
         """Device-side barrier over the ranks, ordered on the current stream (no host block)."""
@@ -126,12 +138,16 @@ class ShardedState:
         S, stride = shard_rows_for(N, world), record_stride(D)
         rec = symm_mem.empty((world * S * stride,), dtype=torch.float32, device=device)
         stg = symm_mem.empty((world * S * stride,), dtype=torch.float32, device=device)
+        rows = symm_mem.empty((world * S * 12,), dtype=torch.float32, device=device)
         rec.zero_()
         stg.zero_()  # the padding rows of a shard are never written and must read as zero gradient
+        rows.zero_()
         h_rec, h_stg = symm_mem.rendezvous(rec, group), symm_mem.rendezvous(stg, group)
+        h_rows = symm_mem.rendezvous(rows, group)
         st = ShardedState(D, N, world, rank, rec, stg, h_rec.buffer_ptrs, h_stg.buffer_ptrs,
-                          lambda: h_rec.barrier(channel=0))
-        st._handles = (h_rec, h_stg)
+                          lambda: h_rec.barrier(channel=0), rows, h_rows.buffer_ptrs)
+        st._handles = (h_rec, h_stg, h_rows)
+        st._group = group
         mc = int(h_rec.multicast_ptr or 0)
         st.mc_records = mc or None
         st.barrier()
@@ -144,8 +160,10 @@ class ShardedState:
         S, stride = shard_rows_for(N, world), record_stride(D)
         recs = [torch.zeros((world * S * stride,), dtype=torch.float32, device=device) for _ in range(world)]
         stgs = [torch.zeros((world * S * stride,), dtype=torch.float32, device=device) for _ in range(world)]
+        rows = [torch.zeros((world * S * 12,), dtype=torch.float32, device=device) for _ in range(world)]
         return [ShardedState(D, N, world, r, recs[r], stgs[r], [t.data_ptr() for t in recs],
-                             [t.data_ptr() for t in stgs], lambda: None) for r in range(world)]
+                             [t.data_ptr() for t in stgs], lambda: None, rows[r], [t.data_ptr() for t in rows])
+                for r in range(world)]
 
 
 def shard_rows_for(N: int, world: int, align: int = 128) -> int:
@@ -167,6 +185,49 @@ def sharded_backward_scatter(rz, st: ShardedState, viewmats, Ks, cam_pos, timest
         1 if rz.aa else 0, ptr(rz.radii), ptr(rz.conics), *rz.grad_args(), st.world, st.rank, st.shard_rows,
         ctypes.cast(arr, ctypes.c_void_p), ptr(rz.status), torch.cuda.current_stream().cuda_stream),
         "ubs_fused_project_bwd_scatter")
+
+
+@torch.no_grad()
+def gather_cameras(st: ShardedState, viewmats, Ks, cam_pos, timestamps, group=None):
+    """All ranks' camera blocks ([world,4,4], [world,3,3], [world,3], [world]) from this rank's ([1,...] each): one small
+    NCCL all-gather, stream-ordered (no host block)."""
+    blk = torch.zeros((32,), dtype=torch.float32, device=viewmats.device)
+    blk[0:16] = viewmats.reshape(-1)
+    blk[16:25] = Ks.reshape(-1)
+    blk[25:28] = cam_pos.reshape(-1)
+    if timestamps is not None:
+        blk[28] = timestamps.reshape(-1)[0]
+    out = torch.empty((st.world, 32), dtype=torch.float32, device=viewmats.device)
+    dist.all_gather_into_tensor(out, blk, group=group)
+    return (out[:, 0:16].reshape(st.world, 4, 4).contiguous(), out[:, 16:25].reshape(st.world, 3, 3).contiguous(),
+            out[:, 25:28].contiguous(), out[:, 28].contiguous() if timestamps is not None else None)
+
+
+@torch.no_grad()
+def sharded_pull_update(rz, st: ShardedState, adam, viewmats_all, Ks_all, cam_pos_all, timestamps_all,
+                        opacity_reg: float = 0.0, scale_reg: float = 0.0, advance: bool = True):
+    """Owner side of the pull form, after a barrier behind every rank's composite_backward(): projection backward over
+    the `world` views for this rank's shard (the views' gradient rows are read from the ranks' peer-mapped buffers),
+    Adam on the shard, new parameters into every rank's records.  *_all: the cameras of all ranks, rank order."""
+    import ctypes
+
+    from ._lib import check, ptr
+
+    assert viewmats_all.shape == (st.world, 4, 4) and Ks_all.shape == (st.world, 3, 3) and cam_pos_all.shape == (st.world, 3)
+    assert all(t is None or (t.is_contiguous() and t.dtype == torch.float32)
+               for t in (viewmats_all, Ks_all, cam_pos_all, timestamps_all))
+    if advance:
+        adam.step_count += 1
+    cols = (ctypes.c_double * st.stride)(*adam.lr_columns())
+    recs = (ctypes.c_void_p * st.world)(*st.peer_records)
+    rows = (ctypes.c_void_p * st.world)(*st.peer_rows)
+    check(rz.lib.ubs_fused_project_bwd_adam_pull(
+        st.N, st.D, st.world, st.rank, st.shard_rows, ctypes.cast(recs, ctypes.c_void_p),
+        ctypes.cast(rows, ctypes.c_void_p), ptr(viewmats_all), ptr(Ks_all), ptr(cam_pos_all), ptr(timestamps_all),
+        rz.W, rz.H, rz.eps2d, 1 if rz.aa else 0, ptr(st.exp_avg), ptr(st.exp_avg_sq),
+        ctypes.cast(cols, ctypes.c_void_p), adam.betas[0], adam.betas[1], adam.eps, adam.step_count,
+        float(opacity_reg), float(scale_reg), torch.cuda.current_stream().cuda_stream),
+        "ubs_fused_project_bwd_adam_pull")
 
 
 @torch.no_grad()

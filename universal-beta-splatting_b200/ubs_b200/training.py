@@ -276,6 +276,9 @@ class TrainStep:
         self.v_ra = torch.zeros_like(rz.render_alphas)  # the loss does not depend on alpha
         self.loss_out = torch.empty((3,), dtype=torch.float32, device=dev)
         self.v_records = None
+        # sharded pull form: the cameras of ALL ranks for the coming step, ([world,4,4], [world,3,3], [world,3], [world] or
+        # None), when the caller knows them; otherwise step() all-gathers them
+        self.all_cameras = None
 
     @torch.no_grad()
     def step(self, records: Tensor, viewmats, Ks, cam_pos, timestamps, backgrounds, gt: Tensor, gt_layout="NCHW",
@@ -316,6 +319,21 @@ class TrainStep:
         if self.sharded is not None:
             st = self.sharded
             assert records.data_ptr() == st.records.data_ptr(), "step() must be given ShardedState.records"
+            if st.exchange == "pull":
+                # the 48-byte screen-space gradient rows are what crosses NVLink: the owner of a shard reads all views'
+                # rows of its primitives, runs projection backward + Adam for them and stores the new rows everywhere
+                if rz.v_rows is not st.rows:
+                    st.attach(rz)
+                cams = (self.all_cameras if self.all_cameras is not None else
+                        parallel.gather_cameras(st, viewmats, Ks, cam_pos, timestamps, self.group))
+                rz.composite_backward(backgrounds, self.v_rc, self.v_ra)
+                with rz._stage("barrier"):
+                    st.barrier()  # every rank's rows are complete
+                with rz._stage("pull_bwd_adam_gather"):
+                    parallel.sharded_pull_update(rz, st, self.adam, *cams, opacity_reg, scale_reg)
+                with rz._stage("barrier"):
+                    st.barrier()  # every shard's new parameters have landed in my records; my rows have been read
+                return self.loss_out
             rz.composite_backward(backgrounds, self.v_rc, self.v_ra)
             with rz._stage("bwd_scatter"):
                 parallel.sharded_backward_scatter(rz, st, viewmats, Ks, cam_pos, timestamps)
