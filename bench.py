@@ -642,7 +642,8 @@ def run_ours(args, rank, local_rank, world):
               2 * N * rec_b + vis * 76)
     stage_roof["rasterize_bwd"] = {"bound": "fp32", "ms": stages_train.get("rasterize_bwd", (0, float("nan")))[1],
                                    "slots": 9.0 * counts["E_cull"] + 45.0 * counts["E_acc"],
-                                   "traffic": traffic.get("rasterize_bwd3_kernel")}
+                                   "traffic": traffic.get("rasterize_bwd3_pairlane_kernel"),
+                                   "kernel": "rasterize_bwd3_pairlane_kernel<4, 3, rows>"}
     hbm_stage("adam_step", stages_full.get("adam_step", (0, float("nan")))[1], 7 * N * rec_b)
     # projection backward with the Adam epilogue: read params + 2 moments, write them back, + the screen-space gradients
     hbm_stage("fused_project_bwd_adam", stages_full.get("fused_project_bwd_adam", (0, float("nan")))[1],
