@@ -306,6 +306,9 @@ int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const f
                           int rows_form,       /* 1: as ubs_rasterize_bwd_rows writes them (moment form),
                                                   0: as ubs_pack_gradient_rows builds them from separate arrays */
                           float *v_records,    /* [N, stride] */
+                          float *v_viewmats,   /* NULL, or [C,4,4]: gradient of the world-to-camera matrices through
+                                                  the projection (fully_fused_projection_bwd.cu:178-201; zeroed by
+                                                  the callee) -- _wrapper.py:898 `viewmats_requires_grad` */
                           int activated, const float *query, /* as in ubs_fused_project_fwd */
                           const int32_t *skip_flag, /* NULL, or the `status` of the frame's tile-list build: when
                                                        status[0] != 0 (the frame lost pairs to the capacity bound) the

@@ -127,9 +127,9 @@ def chain_grads(scene, cam, bg, v_rc, v_ra, keep=None):
             R["isect_offsets"], R["flatten_ids"], R["render_alphas"], R["last_ids"], v_rc, v_ra)
         tri = ([0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2])
         cov6 = v3[..., tri[0], tri[1]].contiguous()
-        g_m3, g_cov6, _, _, _ = C_.fully_fused_projection_bwd(
+        g_m3, g_cov6, _, _, g_view = C_.fully_fused_projection_bwd(
             m3, cov6, None, None, cam.viewmat[None], cam.K[None], W, H, 0.3, False, R["radii"], R["conics"], None, g2d,
-            torch.zeros_like(R["depths"]), gcon, None, False)
+            torch.zeros_like(R["depths"]), gcon, None, keep is not None)  # + v_viewmats for the callers that keep them
         g_v3 = torch.zeros_like(v3)
         g_v3[:, tri[0], tri[1]] = g_cov6
         g_mu, g_covar, g_o, g_bc = C_.cond_mean_convariance_opacity_bwd(
@@ -143,7 +143,8 @@ def chain_grads(scene, cam, bg, v_rc, v_ra, keep=None):
         if keep is not None:  # intermediate results for the golden fixtures
             keep.update(cond_means=m3, cond_covars=v3, cond_opac=o3, v_means2d=g2d, v_conics=gcon, v_colors=gcol,
                         v_opacities=gop, v_betas=gbe, v_cond_means=g_m3, v_cond_cov6=g_cov6, v_mu=g_mu,
-                        v_covar=g_covar, v_opac_act=g_o, v_beta_cond=g_bc, v_scale_act=g_s, v_rot=g_rot)
+                        v_covar=g_covar, v_opac_act=g_o, v_beta_cond=g_bc, v_scale_act=g_s, v_rot=g_rot,
+                        v_viewmats=g_view)
     # torch glue backward (activations, cat)
     torch.autograd.backward([s_act, o_act, b_act, mu], [g_s, g_o, g_b, g_mu])
     return [xyz.grad, mean.grad, gcol[0], opacity.grad, beta.grad, scale.grad, g_lt], R

@@ -184,6 +184,40 @@ def test_two_threads_two_streams_render_concurrently():
         assert torch.equal(rc, want[k][0]) and torch.equal(ra, want[k][1]), (tid, rep, k)
 
 
+@pytest.mark.parametrize("D,N,W,H", [(6, 50000, 480, 360), (7, 30000, 400, 300)])
+def test_fused_viewmat_gradient_matches_reference_projection_backward(D, N, W, H):
+    """viewmats.requires_grad on the fused path (`_wrapper.py:898`): the gradient of the world-to-camera matrix through
+    the projection, against the reference's fully_fused_projection_bwd(viewmats_requires_grad=True) inside the reference
+    chain (the view direction of the conditioning is detached in both, scene/beta_model.py:675-690)."""
+    ref = _ref()
+    from test_gpu_backward import _assert_grad_close
+    from ubs_b200 import fused, synth
+
+    scene = synth.make_scene(N, D, seed=61 + D).to("cuda")
+    cam = synth.make_cameras(1, W, H, seed=4, timestamps=[0.6], device="cuda")[0]
+    bg = torch.tensor([0.2, 0.5, 0.7], device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(8)
+    v_rc = torch.randn(1, H, W, 3, device="cuda", generator=g) / (H * W)
+    v_ra = torch.randn(1, H, W, 1, device="cuda", generator=g) / (H * W)
+    keep = {}
+    ref_grads, _ = ref.chain_grads(scene, cam, bg, v_rc, v_ra, keep=keep)
+    r_view = keep["v_viewmats"]
+
+    rec = fused.pack_records(D, *scene.tensors()).requires_grad_(True)
+    vm = cam.viewmat[None].clone().requires_grad_(True)
+    rz = fused.FusedRasterizer(D, N, W, H, n_cams=1)
+    ts = torch.tensor([cam.timestamp], device="cuda") if D == 7 else None
+    rc, ra = fused.render(rec, rz, vm, cam.K[None], cam.cam_pos[None], ts, bg[None])
+    torch.autograd.backward((rc, ra), (v_rc, v_ra))
+    assert vm.grad is not None and vm.grad.shape == (1, 4, 4)
+    _assert_grad_close("v_viewmats", vm.grad[:, :3, :], r_view[:, :3, :], rtol=5e-3)
+    assert (vm.grad[:, 3, :] == 0).all()
+    # the parameter gradients are those of the plain instantiation
+    mine = fused.unpack_records(D, rec.grad)
+    for name, a, b in zip(("xyz", "mean", "rgb", "opacity", "beta", "scale", "l_triangle"), mine, ref_grads):
+        _assert_grad_close(name, a, b.reshape(a.shape), rtol=3e-3)
+
+
 def test_splat_rows_equal_the_separate_arrays_and_both_compositing_entries_agree():
     """The fused projection writes every visible primitive's screen-space record twice: as the separate arrays of the
     reference (radii, means2d, conics, ...) and as one 48-byte row (`splats`) that the compositing kernels gather from.

@@ -278,6 +278,7 @@ struct BwdOpts {
     const int32_t *skip_flag;  // NULL, or the `status` word of the frame's tile-list build
     const float *v_rows;       // [C, N, 12] screen-space gradient rows (layout: include/ubs_b200.h)
     int moment_form;           // rows of ubs_rasterize_bwd_rows (1) or of ubs_pack_gradient_rows (0)
+    float *v_viewmats;         // POSE instantiation: [C, 4, 4] gradient of the world-to-camera matrices (zeroed by the host)
 };
 
 // a 48-byte gradient row with all ten gradient slots +-0: the primitive received nothing from that view
@@ -305,7 +306,12 @@ __device__ __forceinline__ bool pull_row_nonzero(const float *row) {
 // from every rank's v_rows with one bulk copy per rank (6 KB each, over NVLink) next to the record and moment tiles;
 // visibility is "the row is non-zero", the conic is recomputed (the forward outputs of the other ranks' cameras are not
 // here), and the updated record tile goes to every rank with one bulk store each.
-template <int D, int MINB, bool ADAM, bool PULL = false>
+//
+// POSE = true (plain form only): also the gradient of the C world-to-camera matrices through the projection
+// (fully_fused_projection_bwd.cu:178-201 -- not through the view direction of the conditioning, which the reference
+// detaches): per-(camera, primitive) contributions are summed in shared memory and leave as one atomic per CTA and entry.
+constexpr int kPoseCams = 16;  // cameras with a shared-memory accumulator per CTA (more: global atomics per thread)
+template <int D, int MINB, bool ADAM, bool PULL = false, bool POSE = false>
 __global__ void __launch_bounds__(kFusedThreads, MINB)
 fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in, const float *__restrict__ viewmats,
                          const float *__restrict__ Ks, const float *__restrict__ cam_pos,
@@ -315,6 +321,11 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
                          float *__restrict__ exp_avg_sq, const AdamParams adam, const ScatterDst scatter,
                          const BwdOpts opts, const PullSrc pull) {
     static_assert(!PULL || ADAM, "the pull form updates the parameters");
+    static_assert(!POSE || (!ADAM && !PULL), "camera gradients come out of the plain form");
+    __shared__ float s_pose[POSE ? kPoseCams * 12 : 1];
+    if constexpr (POSE) {
+        for (int k = threadIdx.x; k < kPoseCams * 12; k += kFusedThreads) s_pose[k] = 0.f;  // visible after the barriers below
+    }
     constexpr int Cd = D - 3, M = NdDims<D>::M;
     // the frame this gradient belongs to lost pairs to the capacity bound (isect.cuh: report_truncation): with ADAM the
     // update is not applied at all, otherwise the view contributes a zero gradient (it is dropped from the batch)
@@ -522,8 +533,20 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
                 v_o = v_o * comp;
             }
             float v_mean[3] = {0.f, 0.f, 0.f}, v_s6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            project_splat_vjp(cam, mean, s6, width, height, eps2d, conic, calc_comp ? &comp : nullptr, vm, v_d, vc,
-                              calc_comp ? &v_comp : nullptr, v_mean, v_s6, nullptr, nullptr);
+            if constexpr (POSE) {
+                float vR[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, vt[3] = {0.f, 0.f, 0.f};
+                project_splat_vjp(cam, mean, s6, width, height, eps2d, conic, calc_comp ? &comp : nullptr, vm, v_d, vc,
+                                  calc_comp ? &v_comp : nullptr, v_mean, v_s6, vR, vt);
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    const float v = k < 9 ? vR[k] : vt[k - 9];
+                    if (cid < kPoseCams) atomicAdd(&s_pose[cid * 12 + k], v);
+                    else atomicAdd(opts.v_viewmats + cid * 16 + (k < 9 ? (k / 3) * 4 + k % 3 : (k - 9) * 4 + 3), v);
+                }
+            } else {
+                project_splat_vjp(cam, mean, s6, width, height, eps2d, conic, calc_comp ? &comp : nullptr, vm, v_d, vc,
+                                  calc_comp ? &v_comp : nullptr, v_mean, v_s6, nullptr, nullptr);
+            }
             // index-backward of the 3x3 -> 6 gather: only the upper triangle receives gradient (rendering.py:55-56)
             const float gV[9] = {v_s6[0], v_s6[1], v_s6[2], 0.f, v_s6[3], v_s6[4], 0.f, 0.f, v_s6[5]};
             float g_mu1[3], g_mu2[Cd], g11[9], g12[3 * Cd], g21[Cd * 3], g22[Cd * Cd], go, gb[Cd];
@@ -632,6 +655,13 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
 
     // ---- stage the gradient records in shared memory and write them with one TMA bulk store --------------------
     __syncthreads();  // all record reads done; reuse s_rec
+    if constexpr (POSE) {
+        for (int k = threadIdx.x; k < min(C, kPoseCams) * 12; k += kFusedThreads) {
+            const int cid = k / 12, e = k - cid * 12;
+            const float v = s_pose[k];
+            if (v != 0.f) atomicAdd(opts.v_viewmats + cid * 16 + (e < 9 ? (e / 3) * 4 + e % 3 : (e - 9) * 4 + 3), v);
+        }
+    }
     if ((int)threadIdx.x < n_here) {  // zero rows for the culled primitives (every row, then the live ones overwrite)
         float4 *dst = reinterpret_cast<float4 *>(s_rec + threadIdx.x * STRIDE);
 #pragma unroll
@@ -722,7 +752,7 @@ extern "C" int ubs_fused_project_fwd(int C, int64_t N, int D, const float *recor
 extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const float *viewmats,
                                      const float *Ks, const float *cam_pos, const float *timestamps, int width,
                                      int height, float eps2d, int calc_compensations, const int32_t *radii,
-                                     const float *conics, const float *v_rows, int rows_form, float *v_records, int activated, const float *query,
+                                     const float *conics, const float *v_rows, int rows_form, float *v_records, float *v_viewmats, int activated, const float *query,
                                      const int32_t *skip_flag, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "fused_project_bwd: bad sizes");
@@ -741,7 +771,20 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
     const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams unused{};
     const ScatterDst no_scatter{};
-    const BwdOpts opts{activated, query, skip_flag, v_rows, rows_form};
+    const BwdOpts opts{activated, query, skip_flag, v_rows, rows_form, v_viewmats};
+    if (v_viewmats != nullptr) {
+        UBS_CUDA_TRY(cudaMemsetAsync(v_viewmats, 0, sizeof(float) * 16 * C, s));
+        if (D == 6)
+            fused_project_bwd_kernel<6, 2, false, false, true><<<gx, kFusedThreads, smem, s>>>(
+                C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
+                calc_compensations, radii, conics, v_records, nullptr, nullptr, unused, no_scatter, opts, PullSrc{});
+        else
+            fused_project_bwd_kernel<7, 2, false, false, true><<<gx, kFusedThreads, smem, s>>>(
+                C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
+                calc_compensations, radii, conics, v_records, nullptr, nullptr, unused, no_scatter, opts, PullSrc{});
+        UBS_LAUNCH_CHECK("fused_project_bwd_pose_kernel");
+        return UBS_OK;
+    }
     if (D == 6)
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             C, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
@@ -777,7 +820,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
     const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
     const size_t smem = (size_t)3 * kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
-    const BwdOpts opts{0, nullptr, skip_flag, v_rows, rows_form};
+    const BwdOpts opts{0, nullptr, skip_flag, v_rows, rows_form, nullptr};
     if (D == 6) {
         UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<6, 3, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -831,7 +874,7 @@ extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *reco
     const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
     const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams unused{};
-    const BwdOpts opts{0, nullptr, skip_flag, v_rows, rows_form};
+    const BwdOpts opts{0, nullptr, skip_flag, v_rows, rows_form, nullptr};
     if (D == 6)
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             1, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
@@ -884,7 +927,7 @@ extern "C" int ubs_fused_project_bwd_adam_pull(int64_t N, int D, int world, int 
     const int stride = UBS_RECORD_STRIDE(D);
     const size_t smem = ((size_t)3 * kFusedThreads * stride + (size_t)world * kFusedThreads * 12) * sizeof(float);
     const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
-    const BwdOpts opts{0, nullptr, nullptr, nullptr, 1};
+    const BwdOpts opts{0, nullptr, nullptr, nullptr, 1, nullptr};
     const float *records = pull.records[rank] + row0 * stride;
 #define UBS_PULL_LAUNCH(DD)                                                                                            \
     do {                                                                                                               \

@@ -303,11 +303,13 @@ class FusedRasterizer:
                  backgrounds: Optional[Tensor], v_render_colors: Tensor, v_render_alphas: Tensor,
                  v_records: Optional[Tensor] = None, adam=None, opacity_reg: float = 0.0,
                  scale_reg: float = 0.0, activated: bool = False, query: Optional[Tensor] = None,
-                 alphas: Optional[Tensor] = None) -> Optional[Tensor]:
+                 alphas: Optional[Tensor] = None, v_viewmats: Optional[Tensor] = None) -> Optional[Tensor]:
         """Gradient of the most recent forward() w.r.t. the packed records ([N, stride], same layout).
         Must be called before the next forward(): it reuses that frame's tile lists and screen-space records.
         With `adam` (a training.PackedAdam) the optimiser step is applied inside the projection-backward kernel:
-        `records` and the moments are updated in place, no gradient buffer is produced and None is returned."""
+        `records` and the moments are updated in place, no gradient buffer is produced and None is returned.
+        v_viewmats: None, or a [C,4,4] tensor that receives the gradient of the world-to-camera matrices through the
+        projection (what fully_fused_projection hands back with viewmats_requires_grad, _wrapper.py:898)."""
         lib, s = self.lib, torch.cuda.current_stream().cuda_stream
         C, N, D = self.C, self.N, self.D
         self.composite_backward(backgrounds, v_render_colors, v_render_alphas, alphas)
@@ -329,7 +331,8 @@ class FusedRasterizer:
         if v_records is None:
             v_records = torch.empty_like(records)
         with self._stage("fused_project_bwd"):
-            self.project_backward_rows(records, viewmats, Ks, cam_pos, timestamps, v_records, 0, N, activated, query)
+            self.project_backward_rows(records, viewmats, Ks, cam_pos, timestamps, v_records, 0, N, activated, query,
+                                       v_viewmats)
         return v_records
 
     @torch.no_grad()
@@ -366,10 +369,13 @@ class FusedRasterizer:
 
     @torch.no_grad()
     def project_backward_rows(self, records, viewmats, Ks, cam_pos, timestamps, v_records, begin: int, count: int,
-                              activated: bool = False, query: Optional[Tensor] = None):
+                              activated: bool = False, query: Optional[Tensor] = None,
+                              v_viewmats: Optional[Tensor] = None):
         """Second half of backward() for primitives [begin, begin + count): gradient records of those rows from
         self.v_*.  Row ranges are independent, so a caller can pipeline them against a collective (one camera)."""
         assert self.C == 1 or (begin == 0 and count == self.N), "row ranges need the [C, N] arrays to be [1, N]"
+        assert v_viewmats is None or (begin == 0 and count == self.N and v_viewmats.shape == (self.C, 4, 4) and
+                                      v_viewmats.is_contiguous() and v_viewmats.dtype == torch.float32)
         if count == 0:
             return
         sl = slice(begin, begin + count)
@@ -377,7 +383,7 @@ class FusedRasterizer:
         check(self.lib.ubs_fused_project_bwd(
             self.C, count, self.D, ptr(records[sl]), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), self.W,
             self.H, self.eps2d, 1 if self.aa else 0, ptr(self.radii[:, sl]), ptr(self.conics[:, sl]),
-            *self.grad_args(sl), ptr(v_records[sl]), 1 if activated else 0,
+            *self.grad_args(sl), ptr(v_records[sl]), ptr(v_viewmats), 1 if activated else 0,
             ptr(None if query is None else query[sl]), ptr(self.status),
             torch.cuda.current_stream().cuda_stream), "ubs_fused_project_bwd")
 
@@ -518,12 +524,13 @@ class _FusedRender(torch.autograd.Function):
             rz._poll_count()
             raise UbsError("the frame being differentiated was truncated (pair capacity exceeded); render it again -- "
                            "the buffers have been grown to %d pairs" % rz.capacity)
+        v_view = torch.empty_like(viewmats) if ctx.needs_input_grad[2] else None
         v_records = rz.backward(records, viewmats, Ks, cam_pos, timestamps, backgrounds, v_rc, v_ra,
-                                activated=ctx.activated, query=query, alphas=ra)
+                                activated=ctx.activated, query=query, alphas=ra, v_viewmats=v_view)
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[6]:
             v_bg = (v_rc * (1.0 - ra)).sum(dim=(1, 2))
-        return v_records, None, None, None, None, None, v_bg, None, None, None
+        return v_records, None, v_view, None, None, None, v_bg, None, None, None
 
 
 def render(records: Tensor, rz: FusedRasterizer, viewmats: Tensor, Ks: Tensor, cam_pos: Tensor,
