@@ -90,3 +90,51 @@ def test_conditioning_fwd_bwd(D):
         bad = (num / den > GRAD_RTOL).float().mean().item()
         assert bad < 2e-3, "%s: %.4f%% of primitives exceed rel %g" % (name, 100 * bad, GRAD_RTOL)
         assert _rel_err(mine, theirs) < GRAD_RTOL, name
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_companion_operators_accept_half_and_bfloat16(dtype):
+    """The reference dispatches K1-K4 over half / bfloat16 too (cond_mean_convariance_opacity_fwd.cu:330,
+    rot_scale_l_triangle_to_covar_fwd.cu:216).  Here reduced-precision inputs are widened, computed by the float32
+    kernels and narrowed back: outputs and gradients arrive in the input type and equal the float32 results of the same
+    (already rounded) inputs after one rounding; K1 / K2, which have no cancellation, also agree with the reference's own
+    reduced-precision kernels to a few units of the type's precision."""
+    ref = _ref()
+    C_ = ref.load()
+    from ubs_b200 import ops, synth
+
+    D, N = 6, 5000
+    sc = synth.make_scene(N, D, seed=12).to("cuda")
+    lt = (0.3 * sc.l_triangle).to(dtype)
+    scale = torch.nn.functional.softplus(sc.scale).to(dtype)
+    ri, rj = ref.tril_rest(D, "cuda")
+    lt_l, scale_l = lt.clone().requires_grad_(True), scale.clone().requires_grad_(True)
+    rot = ops.l_triangle_to_rotmat(lt_l[:, :3])
+    cov = ops.rot_scale_l_triangle_to_covar(rot, scale_l, lt_l, ri, rj, False)
+    assert rot.dtype == dtype and cov.dtype == dtype and cov.shape == (N, D, D)
+    # against float32 on the same inputs
+    rot32 = ops.l_triangle_to_rotmat(lt.float()[:, :3].contiguous())
+    cov32 = ops.rot_scale_l_triangle_to_covar(rot32, scale.float(), lt.float(), ri, rj, False)
+    assert torch.equal(rot, rot32.to(dtype))
+    eps = torch.finfo(dtype).eps
+    assert ((cov.float() - cov32).abs() <= 4 * eps * cov32.abs().amax(dim=(1, 2), keepdim=True)).all()
+    # against the reference's reduced-precision instantiations
+    r_rot = C_.l_triangle_to_rotmat_fwd(lt[:, :3].contiguous())
+    assert r_rot.dtype == dtype and torch.equal(r_rot, rot.detach())
+    r_cov = C_.rot_scale_l_triangle_to_covar_fwd(r_rot, scale, lt, ri, rj, False)
+    tol = 16 * eps * cov32.abs().amax(dim=(1, 2), keepdim=True)
+    assert ((r_cov.float() - cov.detach().float()).abs() <= tol).all()
+    # conditioning + gradients in the input type
+    mean = torch.cat([sc.xyz, sc.mean], dim=-1).to(dtype)
+    o = torch.sigmoid(sc.opacity).to(dtype)
+    b = (4.0 * torch.exp(sc.beta))[:, 1:].contiguous().to(dtype)
+    q = torch.nn.functional.normalize(torch.randn(N, D - 3, device="cuda"), dim=-1).to(dtype)
+    m3, v3, o3 = ops.cond_mean_convariance_opacity(mean, cov, o, b, q)
+    assert m3.dtype == v3.dtype == o3.dtype == dtype and v3.shape == (N, 3, 3)
+    m32, v32, o32 = ops.cond_mean_convariance_opacity(mean.float(), cov.detach().float(), o.float(), b.float(), q.float())
+    assert torch.equal(m3.detach(), m32.to(dtype)) and torch.equal(o3.detach(), o32.to(dtype))
+    (m3.float().sum() + v3.float().sum() + o3.float().sum()).backward()
+    assert lt_l.grad is not None and lt_l.grad.dtype == dtype and scale_l.grad.dtype == dtype
+    assert torch.isfinite(lt_l.grad.float()).all() and torch.isfinite(scale_l.grad.float()).all()
+    with pytest.raises(RuntimeError):
+        ops.l_triangle_to_rotmat(lt.double()[:, :3].contiguous())

@@ -20,6 +20,25 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _storage_types(fn):
+    """The reference instantiates K1-K4 for half and bfloat16 as well (AT_DISPATCH_FLOATING_TYPES_AND2,
+    cond_mean_convariance_opacity_fwd.cu:330, rot_scale_l_triangle_to_covar_fwd.cu:216, l_triagnle_to_rotmat_fwd.cu:50):
+    storage in the reduced type, transcendentals in float.  Here such inputs are widened once, the float32 kernels run,
+    and outputs (and, through autograd's cast nodes, gradients) come back in the input's type -- every intermediate is
+    at least as precise as the reference's.  float64 has no instantiation (the caller is float32): rejected by _req."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        dt = next((a.dtype for a in args if isinstance(a, Tensor) and a.is_floating_point()), None)
+        if dt not in (torch.float16, torch.bfloat16):
+            return fn(*args, **kw)
+        out = fn(*[a.float() if isinstance(a, Tensor) and a.dtype == dt else a for a in args], **kw)
+        return tuple(o.to(dt) for o in out) if isinstance(out, tuple) else out.to(dt)
+
+    return wrapped
+
+
 def _req(t: Tensor, name: str, dtype=torch.float32) -> Tensor:
     if not isinstance(t, Tensor) or not t.is_cuda:
         raise RuntimeError("%s must be a CUDA tensor (ubs_b200 has no CPU path)" % name)
@@ -397,6 +416,7 @@ class _LTriangleToRotmat(torch.autograd.Function):
         return v_lt
 
 
+@_storage_types
 def l_triangle_to_rotmat(l_triangle: Tensor) -> Tensor:
     """[N,3] skew parameters -> [N,3,3] first-order rotation I + A (cuda/_wrapper.py:34-36)."""
     assert l_triangle.shape[1] == 3, l_triangle.shape
@@ -445,6 +465,7 @@ class _RotScaleLTriangleToCovar(torch.autograd.Function):
         return v_rot, v_scale, v_lt, None
 
 
+@_storage_types
 def rot_scale_l_triangle_to_covar(rot: Tensor, scale: Tensor, l_triangle: Tensor, rest_i: Tensor, rest_j: Tensor,
                                   spatial_block: bool = False) -> Tensor:
     """Sigma = L L^T (cuda/_wrapper.py:39-55).  D in [4, 8]."""
@@ -493,6 +514,7 @@ class _CondMeanConvarianceOpacity(torch.autograd.Function):
         return v_means, v_covars, v_opac, v_betas, None
 
 
+@_storage_types
 def cond_mean_convariance_opacity(means: Tensor, covars: Tensor, opacities: Tensor, betas: Tensor,
                                   query: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     """Condition the D-dim primitive on `query` (cuda/_wrapper.py:18-31).  means [N,D], covars [N,D,D],
