@@ -119,6 +119,22 @@ parallel.pipelined_backward(rz, rec, None, None, None, None, None, None, None, o
                             lambda b, c: seen.append((b, c)), batch_size=world)
 assert rz.composited and seen == parallel.row_chunks(1000, 3) and sum(c for _, c in seen) == 1000
 assert torch.allclose(out, rec * sum(r + 1 for r in range(world)) / world)
+# pull form of the sharded step, host side: every rank ends up with all ranks' camera blocks in rank order, and the
+# shard bookkeeping of ShardedState (built from ordinary tensors) covers the rows exactly once
+class St: pass
+st = St(); st.world = world
+vm = torch.eye(4)[None] * (rank + 1); K3 = torch.full((1, 3, 3), float(rank)); cp = torch.tensor([[rank, 2.0 * rank, -1.0]])
+ts = torch.tensor([0.25 * (rank + 1)])
+vms, Ks_, cps, tss = parallel.gather_cameras(st, vm, K3, cp, ts)
+assert vms.shape == (world, 4, 4) and Ks_.shape == (world, 3, 3) and cps.shape == (world, 3) and tss.shape == (world,)
+for r in range(world):
+    assert torch.equal(vms[r], torch.eye(4) * (r + 1)) and torch.equal(Ks_[r], torch.full((3, 3), float(r)))
+    assert torch.equal(cps[r], torch.tensor([r, 2.0 * r, -1.0])) and float(tss[r]) == 0.25 * (r + 1)
+assert parallel.gather_cameras(st, vm, K3, cp, None)[3] is None
+states = parallel.ShardedState.create_local_group(6, 1000, world, device="cpu")
+assert all(s.exchange == "pull" and s.rows.shape == (1, 1000, 12) and len(s.peer_rows) == world for s in states)
+spans = [s.my_rows() for s in states]
+assert sum(n for _, n in spans) == 1000 and all(b == r * states[0].shard_rows for r, (b, _) in enumerate(spans))
 cams = parallel.shard_cameras(7, world, rank)
 got = [None] * world
 dist.all_gather_object(got, cams)

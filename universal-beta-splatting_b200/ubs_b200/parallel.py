@@ -197,8 +197,9 @@ def gather_cameras(st: ShardedState, viewmats, Ks, cam_pos, timestamps, group=No
     blk[25:28] = cam_pos.reshape(-1)
     if timestamps is not None:
         blk[28] = timestamps.reshape(-1)[0]
-    out = torch.empty((st.world, 32), dtype=torch.float32, device=viewmats.device)
-    dist.all_gather_into_tensor(out, blk, group=group)
+    flat = torch.empty((st.world * 32,), dtype=torch.float32, device=viewmats.device)
+    dist.all_gather_into_tensor(flat, blk, group=group)  # concatenation form: accepted by NCCL and gloo alike
+    out = flat.view(st.world, 32)
     return (out[:, 0:16].reshape(st.world, 4, 4).contiguous(), out[:, 16:25].reshape(st.world, 3, 3).contiguous(),
             out[:, 25:28].contiguous(), out[:, 28].contiguous() if timestamps is not None else None)
 
