@@ -20,6 +20,13 @@
 namespace ubs {
 namespace {
 
+__device__ __forceinline__ float rcp_1ulp(float b) {  // b > 0, normal
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return fmaf(fmaf(-b, r, 1.f), r, r);
+}
+
+
 constexpr int kR = 5;              // window radius (11 taps)
 constexpr int kTX = 32, kTY = 32;  // outputs per CTA
 constexpr int kIN = kTX + 2 * kR;  // 42 staged rows / columns
@@ -145,7 +152,9 @@ ssim_fwd_kernel(int CH, int H, int W, ImageView img, ImageView gt, Window win, f
                     const float sig1 = acc[1][o] - mu1_sq, sig2 = acc[3][o] - mu2_sq, sig12 = acc[4][o] - mu12;
                     const float A1 = 2.f * mu12 + C1, A2 = 2.f * sig12 + C2;
                     const float B1 = mu1_sq + mu2_sq + C1, B2 = sig1 + sig2 + C2;
-                    const float inv_b1 = __fdiv_rn(1.f, B1), inv_b2 = __fdiv_rn(1.f, B2);
+                    // B1 >= C1 and B2 >= C2 - rounding: well inside the normal range, so MUFU.RCP + one Newton step
+                    // (<= 1 ulp, 4 instructions) replaces the IEEE division and its slow-path checks
+                    const float inv_b1 = rcp_1ulp(B1), inv_b2 = rcp_1ulp(B2);
                     const float S = (A1 * A2) * (inv_b1 * inv_b2);
                     ssim_acc += S;
                     l1_acc += fabsf(s_x[r0 + o + kR][col + kR] - s_y[r0 + o + kR][col + kR]);
