@@ -1,14 +1,20 @@
 // K11: backward of the per-tile compositing.  Drop-in for rasterize_to_pixels_bwd (rasterize_to_pixels_bwd.cu:16-276):
 // re-walks each tile back to front from T_final / last_ids and produces gradients of means2d, conics, colours,
-// opacities and betas (accumulated into caller-zeroed arrays).
+// opacities and betas (accumulated into caller-zeroed arrays or 48-byte rows).
 //
-// Reduction strategy (the reference does 50 SHFL + up to 8x10 global atomics per (tile, pair)):
-//   1. each warp owns an 8x4 pixel sub-tile and first compacts the batch to the pairs whose sigma < 1 support can
-//      touch it (same cull as the forward pass), so most (warp, pair) combinations cost nothing;
-//   2. for 3 channels, three pairs x 10 gradient components are reduced together with one 31-shuffle transposing
-//      butterfly, after which lane l holds the warp total of component l;
-//   3. 30 lanes add those totals into a shared-memory accumulator [pair][component] in one instruction;
-//   4. after the batch, each thread flushes one pair with at most 10 global atomics -- one set per (tile, pair).
+// Three kernels:
+//   * rasterize_bwd3_pairlane_kernel (RGB; the fused path's kernel, ubs_rasterize_bwd_rows, and the default of
+//     ubs_rasterize_bwd[_splats] at 3 channels): lane = pair, loop = the pixels of a 4x4 block, the sequential walk of a
+//     pixel's pairs as one warp scan of affine maps -- see the comment at the kernel;
+//   * rasterize_bwd_kernel<CH> (other channel counts: depth modes, N-D colour chunks) and rasterize_bwd3_kernel (the
+//     round-1 RGB kernel, UBS_BWD3_VARIANT=0, kept for A/B): lane = pixel.  Their reduction strategy (the reference
+//     does 50 SHFL + up to 8x10 global atomics per (tile, pair)):
+//       1. each warp owns an 8x4 pixel sub-tile and first compacts the batch to the pairs whose sigma < 1 support can
+//          touch it (same cull as the forward pass), so most (warp, pair) combinations cost nothing;
+//       2. for 3 channels, three pairs x 10 gradient components are reduced together with one 31-shuffle transposing
+//          butterfly, after which lane l holds the warp total of component l;
+//       3. 30 lanes add those totals into a shared-memory accumulator [pair][component] in one instruction;
+//       4. after the batch, each thread flushes one pair with at most 10 global atomics -- one set per (tile, pair).
 #include <stdlib.h>
 
 #include "common.cuh"
