@@ -441,7 +441,7 @@ def test_sharded_step_kernels_equal_allreduce_then_adam_bitwise(world, D, N):
             assert float(st.exp_avg[n:].abs().sum()) == 0.0  # padding rows of the last shard never move
 
 
-@pytest.mark.parametrize("world,D,N", [(4, 6, 30011), (2, 7, 20000), (8, 6, 9000)])
+@pytest.mark.parametrize("world,D,N", [(4, 6, 30011), (2, 7, 20000), (8, 6, 9000), (3, 7, 6500), (1, 6, 4000)])
 def test_sharded_pull_step_equals_the_multi_camera_fused_update(world, D, N):
     """Pull form of the sharded step (every rank leaves its view's 48-byte gradient rows in a buffer its peers can read;
     the owner of a shard fetches all views' rows of its primitives, runs projection backward + Adam on them and stores
