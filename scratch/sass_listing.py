@@ -1,4 +1,4 @@
-"""profiles/r2_sass_mnemonics.txt: SASS mnemonic counts per kernel of the built library (cuobjdump -sass)."""
+"""profiles/r2z_sass_mnemonics.txt: SASS mnemonic counts per kernel of the built library (cuobjdump -sass)."""
 import re, subprocess, sys
 lib = "universal-beta-splatting_b200/ubs_b200/lib/libubs_b200.so"
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
@@ -9,7 +9,7 @@ out = ["# SASS mnemonic counts per kernel of libubs_b200.so (sm_100a): `cuobjdum
        "# UBLKCP = TMA bulk copies (cp.async.bulk), SYNCS = mbarrier operations, MATCH = match.any, REDG / RED = reductions without",
        "# return (global atomics), ATOMS / ATOMG = returning shared / global atomics, MUFU = special-function unit.  The last column",
        "# counts tensor-core mnemonics: zero everywhere by design (no stage of the path is a dense contraction).",
-       "# regenerate: python scratch/sass_listing.py > profiles/r2_sass_mnemonics.txt", "",
+       "# regenerate: python scratch/sass_listing.py > profiles/r2z_sass_mnemonics.txt", "",
        "%-58s %6s " % ("kernel", "instr") + " ".join("%6s" % k.split("|")[0][:6] for k in keys[:-1]) + " tensor"]
 for p in parts[1:]:
     name = p.split('\n', 1)[0].strip()
