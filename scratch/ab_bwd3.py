@@ -34,7 +34,7 @@ else:
         outs = []
         for v in os.environ.get("AB_VARIANTS", "0,1,rows").split(","):
             f = "/tmp/ab_bwd3_%s_%s.pt" % (name, v)
-            subprocess.run([sys.executable, __file__, "child", name, f], env=dict(os.environ, UBS_BWD3_VARIANT={"rows": "1", "rows8": "8"}.get(v, v), AB_ROWS="1" if v.startswith("rows") else "0", AB_NAME=v), check=True)
+            subprocess.run([sys.executable, __file__, "child", name, f], env=dict(os.environ, UBS_BWD3_VARIANT={"rows": "1"}.get(v, v), AB_ROWS="1" if v == "rows" else "0", AB_NAME=v), check=True)
             outs.append(torch.load(f).double())
         a, b = outs[0], outs[-1]
         scale = a.abs().amax(dim=0).clamp_min(1e-30)

@@ -958,8 +958,8 @@ int launch_bwd_rows(int C, int64_t N, const int64_t *n_isects, int64_t cap, cons
     const uint32_t tw = (uint32_t)ceil_div(width, kTile), th = (uint32_t)ceil_div(height, kTile);
     dim3 grid(tw, th, (unsigned)C), block(kTilePixels, 1, 1);
     // four pixels in flight per lane at 3 CTAs / SM measured faster than two at 4 CTAs / SM (1.124 against 1.156 ms, cfg3)
-    auto *kern = bwd3_variant() == 8 ? rasterize_bwd3_pairlane_kernel<8, 2, true> : rasterize_bwd3_pairlane_kernel<4, 3, true>;
-    kern<<<grid, block, 0, s>>>(
+    // (eight in flight at 2 CTAs / SM: 2.2 ms -- 128 registers and spills)
+    rasterize_bwd3_pairlane_kernel<4, 3, true><<<grid, block, 0, s>>>(
         C, N, n_isects, cap, nullptr, nullptr, nullptr, nullptr, nullptr, backgrounds, masks, (uint32_t)width,
         (uint32_t)height, tw, th, offsets, flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas,
         nullptr, nullptr, nullptr, nullptr, nullptr, (const float4 *)splats, true, v_rows, skip_flag);
