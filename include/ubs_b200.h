@@ -315,6 +315,17 @@ int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const f
                                                        gradient records are all zero -- the view is dropped */
                           void *stream);
 
+/* ubs_fused_project_bwd with ubs_unpack_records fused in (the drop-in route): the gradient tiles leave the kernel as
+ * the reference's seven separate tensors (layouts as in ubs_unpack_records; any destination may be NULL) and no
+ * gradient record buffer exists.                                                                               */
+int ubs_fused_project_bwd_unpacked(int C, int64_t N, int D, const float *records, const float *viewmats,
+                                   const float *Ks, const float *cam_pos, const float *timestamps, int width,
+                                   int height, float eps2d, int calc_compensations, const int32_t *radii,
+                                   const float *conics, const float *v_rows, int rows_form, float *v_mean,
+                                   float *v_rgb, float *v_opacity, float *v_beta0, float *v_beta_c, float *v_scale,
+                                   float *v_l_triangle, float *v_viewmats, int activated, const float *query,
+                                   const int32_t *skip_flag, void *stream);
+
 /* Packing of the reference's separate per-primitive tensors into records and back (the zero-edit drop-in route,
  * ubs_b200/dropin.py; csrc/pack.cu).  mean [N,D] = xyz | conditional mean (get_mean, scene/beta_model.py:111-113),
  * rgb [N,3], opacity [N], beta0 [N] (spatial beta), beta_c [N,D-3], scale [N,D], l_triangle [N,D(D-1)/2]; values are

@@ -15,6 +15,7 @@
 #include "cond_math.cuh"
 #include "isect.cuh"
 #include "optim.cuh"
+#include "pack.cuh"
 #include "proj_math.cuh"
 
 namespace ubs {
@@ -279,6 +280,7 @@ struct BwdOpts {
     const float *v_rows;       // [C, N, 12] screen-space gradient rows (layout: include/ubs_b200.h)
     int moment_form;           // rows of ubs_rasterize_bwd_rows (1) or of ubs_pack_gradient_rows (0)
     float *v_viewmats;         // POSE instantiation: [C, 4, 4] gradient of the world-to-camera matrices (zeroed by the host)
+    PackSegs v_segs;           // plain form: when v_records is NULL, the gradient tile leaves as the seven separate arrays
 };
 
 // a 48-byte gradient row with all ten gradient slots +-0: the primitive received nothing from that view
@@ -675,6 +677,11 @@ fused_project_bwd_kernel(int C, int64_t N, const float *__restrict__ records_in,
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    if (v_records == nullptr && scatter.shard_rows == 0) {
+        // the drop-in route: gradients straight into the reference's seven tensors (ubs_unpack_records fused in)
+        unpack_tile<D, kFusedThreads>(s_rec, opts.v_segs, base, n_here);
+        return;
+    }
     if (threadIdx.x == 0) {
         float *dst = v_records + base * STRIDE;
         if (scatter.shard_rows > 0) {
@@ -749,17 +756,18 @@ extern "C" int ubs_fused_project_fwd(int C, int64_t N, int D, const float *recor
     return isect_blocksums_from_counts(CN, tiles_per_gauss, workspace, n_isects, s);
 }
 
-extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const float *viewmats,
+static int fused_project_bwd_impl(int C, int64_t N, int D, const float *records, const float *viewmats,
                                      const float *Ks, const float *cam_pos, const float *timestamps, int width,
                                      int height, float eps2d, int calc_compensations, const int32_t *radii,
                                      const float *conics, const float *v_rows, int rows_form, float *v_records, float *v_viewmats, int activated, const float *query,
-                                     const int32_t *skip_flag, void *stream) {
+                                     const int32_t *skip_flag, const ubs::PackSegs &v_segs, void *stream) {
     using namespace ubs;
     UBS_CHECK_ARG(C >= 0 && N >= 0 && width > 0 && height > 0, "fused_project_bwd: bad sizes");
     UBS_CHECK_ARG(D == 6 || D == 7, "fused_project_bwd: D must be 6 or 7 (got %d)", D);
     if (N == 0) return UBS_OK;
     UBS_CHECK_ARG(records && viewmats && Ks && (cam_pos || query) && radii && conics &&
-                      v_rows && v_records,
+                      v_rows && (v_records || v_segs.ptr[0] || v_segs.ptr[1] || v_segs.ptr[2] || v_segs.ptr[3] ||
+                                 v_segs.ptr[4] || v_segs.ptr[5] || v_segs.ptr[6]),
                   "fused_project_bwd: null pointer");
     UBS_CHECK_ARG(D != 7 || timestamps != nullptr || query != nullptr, "fused_project_bwd: D=7 needs timestamps");
     UBS_CHECK_ARG((((uintptr_t)records | (uintptr_t)v_records) & 15) == 0,
@@ -771,7 +779,7 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
     const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams unused{};
     const ScatterDst no_scatter{};
-    const BwdOpts opts{activated, query, skip_flag, v_rows, rows_form, v_viewmats};
+    const BwdOpts opts{activated, query, skip_flag, v_rows, rows_form, v_viewmats, v_segs};
     if (v_viewmats != nullptr) {
         UBS_CUDA_TRY(cudaMemsetAsync(v_viewmats, 0, sizeof(float) * 16 * C, s));
         if (D == 6)
@@ -799,6 +807,35 @@ extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *recor
     return UBS_OK;
 }
 
+extern "C" int ubs_fused_project_bwd(int C, int64_t N, int D, const float *records, const float *viewmats,
+                                     const float *Ks, const float *cam_pos, const float *timestamps, int width,
+                                     int height, float eps2d, int calc_compensations, const int32_t *radii,
+                                     const float *conics, const float *v_rows, int rows_form, float *v_records,
+                                     float *v_viewmats, int activated, const float *query, const int32_t *skip_flag,
+                                     void *stream) {
+    using namespace ubs;
+    UBS_CHECK_ARG(v_records != nullptr || N == 0, "fused_project_bwd: v_records is null");
+    return fused_project_bwd_impl(C, N, D, records, viewmats, Ks, cam_pos, timestamps, width, height, eps2d,
+                                  calc_compensations, radii, conics, v_rows, rows_form, v_records, v_viewmats, activated,
+                                  query, skip_flag, PackSegs{}, stream);
+}
+
+extern "C" int ubs_fused_project_bwd_unpacked(int C, int64_t N, int D, const float *records, const float *viewmats,
+                                              const float *Ks, const float *cam_pos, const float *timestamps, int width,
+                                              int height, float eps2d, int calc_compensations, const int32_t *radii,
+                                              const float *conics, const float *v_rows, int rows_form, float *v_mean,
+                                              float *v_rgb, float *v_opacity, float *v_beta0, float *v_beta_c,
+                                              float *v_scale, float *v_l_triangle, float *v_viewmats, int activated,
+                                              const float *query, const int32_t *skip_flag, void *stream) {
+    using namespace ubs;
+    const PackSegs segs{{v_mean, v_rgb, v_opacity, v_beta0, v_beta_c, v_scale, v_l_triangle}};
+    UBS_CHECK_ARG(v_mean || v_rgb || v_opacity || v_beta0 || v_beta_c || v_scale || v_l_triangle || N == 0,
+                  "fused_project_bwd_unpacked: every destination is null");
+    return fused_project_bwd_impl(C, N, D, records, viewmats, Ks, cam_pos, timestamps, width, height, eps2d,
+                                  calc_compensations, radii, conics, v_rows, rows_form, nullptr, v_viewmats, activated,
+                                  query, skip_flag, segs, stream);
+}
+
 extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *records, const float *viewmats,
                                           const float *Ks, const float *cam_pos, const float *timestamps, int width,
                                           int height, float eps2d, int calc_compensations, const int32_t *radii,
@@ -820,7 +857,7 @@ extern "C" int ubs_fused_project_bwd_adam(int C, int64_t N, int D, float *record
     const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
     const size_t smem = (size_t)3 * kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
-    const BwdOpts opts{0, nullptr, skip_flag, v_rows, rows_form, nullptr};
+    const BwdOpts opts{0, nullptr, skip_flag, v_rows, rows_form, nullptr, PackSegs{}};
     if (D == 6) {
         UBS_CUDA_TRY(cudaFuncSetAttribute(fused_project_bwd_kernel<6, 3, true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -874,7 +911,7 @@ extern "C" int ubs_fused_project_bwd_scatter(int64_t N, int D, const float *reco
     const unsigned gx = (unsigned)ceil_div(N, kFusedThreads);
     const size_t smem = (size_t)kFusedThreads * UBS_RECORD_STRIDE(D) * sizeof(float);
     const AdamParams unused{};
-    const BwdOpts opts{0, nullptr, skip_flag, v_rows, rows_form, nullptr};
+    const BwdOpts opts{0, nullptr, skip_flag, v_rows, rows_form, nullptr, PackSegs{}};
     if (D == 6)
         fused_project_bwd_kernel<6, 3, false><<<gx, kFusedThreads, smem, s>>>(
             1, N, records, viewmats, Ks, cam_pos, timestamps, (uint32_t)width, (uint32_t)height, eps2d,
@@ -927,7 +964,7 @@ extern "C" int ubs_fused_project_bwd_adam_pull(int64_t N, int D, int world, int 
     const int stride = UBS_RECORD_STRIDE(D);
     const size_t smem = ((size_t)3 * kFusedThreads * stride + (size_t)world * kFusedThreads * 12) * sizeof(float);
     const AdamParams a = make_adam_params(N, D, h_lr, beta1, beta2, eps, step, opacity_reg, scale_reg);
-    const BwdOpts opts{0, nullptr, nullptr, nullptr, 1, nullptr};
+    const BwdOpts opts{0, nullptr, nullptr, nullptr, 1, nullptr, PackSegs{}};
     const float *records = pull.records[rank] + row0 * stride;
 #define UBS_PULL_LAUNCH(DD)                                                                                            \
     do {                                                                                                               \

@@ -20,7 +20,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 extern "C" unsigned long long ubs_launch_count(void) { return ubs::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char *ubs_last_error(void) { return ubs::g_err; }
-extern "C" int ubs_version(void) { return 4; }
+extern "C" int ubs_version(void) { return 5; }
 extern "C" int ubs_device_sm_count(void) {
     int dev = 0, n = 0;
     UBS_CUDA_TRY(cudaGetDevice(&dev));

@@ -7,26 +7,13 @@
 // One CTA handles 128 consecutive rows: every source tile [128, w] is a contiguous span of global memory and is read
 // with fully coalesced loads into a shared [128, stride] tile, which then leaves as coalesced 128-bit stores.
 #include "common.cuh"
+#include "pack.cuh"
 
 namespace ubs {
 namespace {
 
 constexpr int kPackRows = 128;
 constexpr int kPackThreads = 256;
-
-struct PackSegs {
-    float *ptr[7];  // mean[N,D] (xyz | conditional mean), rgb[N,3], opacity[N], beta0[N], beta_c[N,D-3], scale[N,D], l_triangle[N,M]
-};
-
-// width and first record column of segment `s` (layout of include/ubs_b200.h)
-template <int D>
-__host__ __device__ constexpr int seg_width(int s) {
-    return s == 0 ? D : s == 1 ? 3 : s == 2 ? 1 : s == 3 ? 1 : s == 4 ? D - 3 : s == 5 ? D : D * (D - 1) / 2;
-}
-template <int D>
-__host__ __device__ constexpr int seg_col(int s) {
-    return s == 0 ? 0 : s == 1 ? D : s == 2 ? D + 3 : s == 3 ? D + 4 : s == 4 ? D + 5 : s == 5 ? 2 * D + 2 : 3 * D + 2;
-}
 
 template <int D, bool PACK>
 __global__ void __launch_bounds__(kPackThreads)

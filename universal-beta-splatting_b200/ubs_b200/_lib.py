@@ -57,6 +57,8 @@ SIGNATURES = {
     "ubs_fused_project_bwd": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_int] +
                               [_P, _P, _P, c_int, _P, _P] + [c_int, _P, _P, _P]),
     "ubs_pack_gradient_rows": (c_int, [c_int64] + [_P] * 8),
+    "ubs_fused_project_bwd_unpacked": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_int] +
+                                       [_P, _P, _P, c_int] + [_P] * 8 + [c_int, _P, _P, _P]),
     "ubs_pack_records": (c_int, [c_int64, c_int] + [_P] * 9),
     "ubs_unpack_records": (c_int, [c_int64, c_int] + [_P] * 9),
     "ubs_l1_ssim_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -287,10 +287,6 @@ class _DropinRender(torch.autograd.Function):
         rz = slot.rz
         if rz.frame_id != ctx.frame_id:
             raise _lib.UbsError("stale frame in the drop-in route (rasteriser slot reused before its backward)")
-        if slot.v_records is None:
-            slot.v_records = torch.empty_like(slot.records)
-        rz.backward(slot.records, viewmats, Ks, None, None, backgrounds, v_rc, v_ra, v_records=slot.v_records,
-                    activated=True, query=query, alphas=ra)
         N, D = rz.N, rz.D
         need = ctx.needs_input_grad
         dev = rz.device
@@ -303,8 +299,9 @@ class _DropinRender(torch.autograd.Function):
              torch.empty((N, D - 3), dtype=f32, device=dev) if need[4] else None,
              torch.empty((N, D), dtype=f32, device=dev) if need[5] else None,
              torch.empty((N, M), dtype=f32, device=dev) if need[6] else None]
-        check(rz.lib.ubs_unpack_records(N, D, ptr(slot.v_records), *[ptr(t) for t in g],
-                                        torch.cuda.current_stream().cuda_stream), "ubs_unpack_records")
+        # the projection backward writes the seven gradients itself (no gradient record buffer, no unpack pass)
+        rz.backward(slot.records, viewmats, Ks, None, None, backgrounds, v_rc, v_ra, activated=True, query=query,
+                    alphas=ra, v_segments=g)
         v_bg = None
         if backgrounds is not None and need[7]:
             v_bg = (v_rc * (1.0 - ra)).sum(dim=(1, 2))

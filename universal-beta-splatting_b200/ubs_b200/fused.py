@@ -303,13 +303,17 @@ class FusedRasterizer:
                  backgrounds: Optional[Tensor], v_render_colors: Tensor, v_render_alphas: Tensor,
                  v_records: Optional[Tensor] = None, adam=None, opacity_reg: float = 0.0,
                  scale_reg: float = 0.0, activated: bool = False, query: Optional[Tensor] = None,
-                 alphas: Optional[Tensor] = None, v_viewmats: Optional[Tensor] = None) -> Optional[Tensor]:
+                 alphas: Optional[Tensor] = None, v_viewmats: Optional[Tensor] = None,
+                 v_segments=None) -> Optional[Tensor]:
         """Gradient of the most recent forward() w.r.t. the packed records ([N, stride], same layout).
         Must be called before the next forward(): it reuses that frame's tile lists and screen-space records.
         With `adam` (a training.PackedAdam) the optimiser step is applied inside the projection-backward kernel:
         `records` and the moments are updated in place, no gradient buffer is produced and None is returned.
         v_viewmats: None, or a [C,4,4] tensor that receives the gradient of the world-to-camera matrices through the
-        projection (what fully_fused_projection hands back with viewmats_requires_grad, _wrapper.py:898)."""
+        projection (what fully_fused_projection hands back with viewmats_requires_grad, _wrapper.py:898).
+        v_segments: None, or seven tensors / Nones (mean [N,D], rgb [N,3], opacity [N], beta0 [N], beta_c [N,D-3],
+        scale [N,D], l_triangle [N,M]): the gradient leaves the projection backward in the reference's separate layout
+        instead of as records (the drop-in route; no v_records is produced, None is returned)."""
         lib, s = self.lib, torch.cuda.current_stream().cuda_stream
         C, N, D = self.C, self.N, self.D
         self.composite_backward(backgrounds, v_render_colors, v_render_alphas, alphas)
@@ -327,6 +331,16 @@ class FusedRasterizer:
                 ptr(adam.exp_avg), ptr(adam.exp_avg_sq), ctypes.cast(cols, ctypes.c_void_p), adam.betas[0], adam.betas[1], adam.eps,
                 adam.step_count, float(opacity_reg), float(scale_reg), ptr(self.status), s),
                 "ubs_fused_project_bwd_adam")
+            return None
+        if v_segments is not None:
+            assert len(v_segments) == 7 and all(t is None or (t.is_contiguous() and t.dtype == torch.float32 and
+                                                               t.shape[0] == N) for t in v_segments)
+            with self._stage("fused_project_bwd"):
+                check(lib.ubs_fused_project_bwd_unpacked(
+                    C, N, D, ptr(records), ptr(viewmats), ptr(Ks), ptr(cam_pos), ptr(timestamps), self.W, self.H,
+                    self.eps2d, 1 if self.aa else 0, ptr(self.radii), ptr(self.conics), *self.grad_args(),
+                    *[ptr(t) for t in v_segments], ptr(v_viewmats), 1 if activated else 0, ptr(query), ptr(self.status),
+                    s), "ubs_fused_project_bwd_unpacked")
             return None
         if v_records is None:
             v_records = torch.empty_like(records)
