@@ -13,7 +13,8 @@ HBM traffic per primitive in between.  Here the three companion operators return
 operations the caller applies to them before `rasterization()` -- `[mask]`, `.squeeze()` -- stay deferred;
 `rasterization()` then recognises its own conditioned tensors, packs the seven activated inputs of the chain into
 records (ONE pass, csrc/pack.cu) and runs the fused kernels (`activated` records, the caller's own `query`), with one
-autograd node whose backward hands gradients to exactly the tensors the chain received.  Any other use of a deferred
+autograd node whose backward hands gradients to exactly the tensors the chain received (the projection backward writes
+the seven gradient tensors itself, ubs_fused_project_bwd_unpacked).  Any other use of a deferred
 tensor (arithmetic, printing, indexing by anything but a primitive mask, ...) materialises it through the stand-alone
 operators -- same values as before, just not fused -- so nothing the reference could do stops working.
 
