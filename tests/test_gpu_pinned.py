@@ -3,6 +3,8 @@ fused, forward and backward), tile masks, depth-channel VALUES of every depth mo
 stale-frame and pair-overflow guards of the fused rasteriser, and bit-exact tile lists at the full BASELINE sizes."""
 import warnings
 
+import math
+
 import pytest
 import torch
 
@@ -147,6 +149,47 @@ def test_tile_masks_forward_and_backward_match_reference_kernels():
                              last_r, v_rc, v_ra)
     for name, a, b in zip(("v_means2d", "v_conics", "v_colors", "v_opacities", "v_betas"), mine, r):
         _assert_grad_close(name, a, b)
+
+
+def test_gradient_row_kernel_with_tile_masks_matches_reference_backward():
+    """ubs_rasterize_bwd_rows (the fused path's RGB backward) driven stand-alone with tile masks and two cameras, its rows
+    decoded as include/ubs_b200.h documents, against the reference's rasterize_to_pixels_bwd on the same lists."""
+    ref = _ref()
+    C_ = ref.load()
+    from test_gpu_backward import _assert_grad_close
+    from ubs_b200 import _lib
+    from ubs_b200._lib import check, ptr
+
+    N, W, H, C = 20000, 333, 250, 2
+    means, covars, opac, betas, colors, viewmats, Ks = _inputs(N, 707, W, H, C)
+    bg = torch.rand(C, 3, device="cuda")
+    R = ref.rasterization_fwd(means, covars, opac, betas, colors, viewmats, Ks, W, H, backgrounds=bg)
+    th, tw = R["isect_offsets"].shape[1:]
+    masks = torch.rand(C, th, tw, device="cuda") < 0.6
+    rc_r, ra_r, last_r = C_.rasterize_to_pixels_fwd(R["means2d"], R["conics"], R["colors"], R["opacities"], R["betas"],
+                                                    bg, masks, W, H, 16, R["isect_offsets"], R["flatten_ids"])
+    v_rc = torch.randn(C, H, W, 3, device="cuda") / (H * W)
+    v_ra = torch.randn(C, H, W, 1, device="cuda") / (H * W)
+    r = C_.rasterize_to_pixels_bwd(R["means2d"], R["conics"], R["colors"], R["opacities"], R["betas"], bg, masks, W, H,
+                                   16, R["isect_offsets"], R["flatten_ids"], ra_r, last_r, v_rc, v_ra)
+    # the 48-byte splat rows the fused projection kernel would have written
+    splats = torch.zeros(C, N, 12, device="cuda")
+    splats[..., 0:2], splats[..., 2], splats[..., 3] = R["means2d"], R["opacities"], R["betas"]
+    splats[..., 4:7], splats[..., 7], splats[..., 8:11] = R["conics"], R["depths"], R["colors"]
+    rows = torch.zeros(C, N, 12, device="cuda")
+    n = torch.tensor([R["flatten_ids"].numel()], dtype=torch.int64, device="cuda")
+    m8 = masks.contiguous().view(torch.uint8)
+    check(_lib.load().ubs_rasterize_bwd_rows(
+        C, N, ptr(n), R["flatten_ids"].numel(), ptr(splats), ptr(bg), ptr(m8), W, H, 16, ptr(R["isect_offsets"]),
+        ptr(R["flatten_ids"]), ptr(ra_r.contiguous()), ptr(last_r.contiguous()), ptr(v_rc), ptr(v_ra), ptr(rows), None,
+        torch.cuda.current_stream().cuda_stream), "ubs_rasterize_bwd_rows")
+    a, b, c = R["conics"].unbind(-1)
+    mine = (torch.stack((2 * a * rows[..., 6] + 2 * b * rows[..., 7], 2 * b * rows[..., 6] + 2 * c * rows[..., 7]), -1),
+            torch.stack((rows[..., 3], 2 * rows[..., 4], rows[..., 5]), -1), rows[..., 0:3], rows[..., 8],
+            rows[..., 9] * math.log(2.0))
+    for name, x, y in zip(("v_means2d", "v_conics", "v_colors", "v_opacities", "v_betas"), mine, r):
+        _assert_grad_close(name, x, y.reshape(x.shape))
+    assert (rows[..., 10:] == 0).all()
 
 
 def _well_conditioned_normals(depth_img, c2w, Ks, noise=1e-4):
